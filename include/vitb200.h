@@ -1,0 +1,156 @@
+/*
+ * vitb200.h — C ABI of libvitb200.so, the sm_100a (B200) kernel library under the ViT hot path of
+ * ambroiseodt/vit-plasticity (ViT Block forward/backward + per-component plasticity estimator).
+ *
+ * The reference has no FFI of its own: every arithmetic op on the path is a PyTorch ATen call made from
+ * `src/vitef/models/transformer/architecture.py` / `transformer/utils.py`. Each entry point below names the
+ * reference call site(s) it replaces. The reference-side binding (a ctypes stub inside a
+ * torch.autograd.Function) is shown in INTEGRATION.md and implemented in vit_plasticity_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - "bf16" buffers are raw 16-bit bfloat16; row-major; leading dimensions (ld*) are in ELEMENTS;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing that outlives the call,
+ *     and returns 0 on success / non-zero on error (message: vb_last_error(), thread-local);
+ *   - nothing here falls back to a CPU or library (cuBLAS/cuDNN) path.
+ */
+#ifndef VITB200_H
+#define VITB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vb_stream_t; /* cudaStream_t */
+
+#define VB_OK 0
+#define VB_ERR_INVALID 1
+#define VB_ERR_CUDA 2
+#define VB_ERR_UNSUPPORTED 3
+
+int vb_version(void);
+const char* vb_last_error(void);
+/* number of kernel launches issued by this library in this process (bench.py's `gpu_launches`) */
+int64_t vb_launch_count(void);
+void vb_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM on tcgen05/TMEM fed by TMA:  C[M,N] = epilogue( sum_k A[m,k] * B[n,k] ), bf16 in, fp32 accumulate.
+ * Replaces nn.Linear / nn.Conv2d(k=s=P) forward (architecture.py:205,236,295,297; transformer/utils.py:91)
+ * and their autograd dgrad / wgrad (`loss.backward()`, apps/vit/train.py:270).
+ *
+ *   a_layout / b_layout: 0 = "K-major": A stored [M,K] (B stored [N,K]), contraction index contiguous;
+ *                        1 = "MN-major": A stored [K,M] (B stored [K,N]), contraction index strided.
+ *   forward  y = x W^T        : A = x  [M,K]  layout 0,  B = W  [N,K]        layout 0
+ *   dgrad    dx = dy W        : A = dy [M,N'] layout 0,  B = W  [N',K'] seen as [K=N', N=K'] layout 1
+ *   wgrad    dW = dy^T x      : A = dy [tokens,N'] seen as [K=tokens, M=N'] layout 1,
+ *                               B = x  [tokens,K'] seen as [K=tokens, N=K'] layout 1
+ * ------------------------------------------------------------------------------------------------ */
+enum vb_epilogue {
+    VB_EPI_BF16 = 0,       /* out = acc (+ bias)                                   out: bf16 [M,N]          */
+    VB_EPI_BF16_RESID = 1, /* out = acc (+ bias) + aux                             aux: bf16 [M,N]          */
+    VB_EPI_BF16_GELU = 2,  /* out2 = z = acc (+ bias); out = gelu_erf(z)           out, out2: bf16 [M,N]    */
+    VB_EPI_BF16_DGELU = 3, /* out = acc * gelu_erf'(aux)                           aux = z: bf16 [M,N]      */
+    VB_EPI_F32 = 4,        /* out = acc (+ bias)                                   out: f32 [M,N]           */
+    VB_EPI_F32_ADD = 5,    /* out += acc   (TMA reduce-add; split_k >= 1)          out: f32 [M,N]           */
+    VB_EPI_SUMSQ = 6       /* sumsq[row / rows_per_sample, col / cols_per_group] += acc^2 ; nothing stored  */
+};
+
+typedef struct vb_gemm_args {
+    const void* a;      /* bf16 */
+    const void* b;      /* bf16 */
+    int64_t lda;        /* row stride of the stored A matrix, elements */
+    int64_t ldb;
+    int32_t a_layout;   /* 0 K-major, 1 MN-major */
+    int32_t b_layout;
+    int32_t m, n, k;
+    int32_t epilogue;   /* enum vb_epilogue */
+    const float* bias;  /* f32 [N] or NULL */
+    const void* aux;    /* bf16 [M,N] (residual or pre-activation) or NULL */
+    int64_t ld_aux;
+    void* out;          /* bf16 or f32 [M,N] (unused for SUMSQ) */
+    int64_t ld_out;
+    void* out2;         /* bf16 [M,N], GELU only */
+    int64_t ld_out2;
+    float* sumsq;       /* f32 [n_samples, n_groups], SUMSQ only (accumulated into; caller zeroes) */
+    int32_t rows_per_sample;
+    int32_t cols_per_group; /* multiple of 128 */
+    int32_t n_groups;
+    int32_t split_k;    /* >= 1; > 1 only with VB_EPI_F32_ADD */
+} vb_gemm_args;
+
+int vb_gemm_bf16(const vb_gemm_args* args, vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (nn.LayerNorm, transformer/utils.py:293; used at architecture.py:347,349 and utils.py:396)
+ * one warp per row, 128-bit accesses, fp32 statistics. x, y: bf16 [rows, cols]; gamma/beta f32 [cols].
+ * ------------------------------------------------------------------------------------------------ */
+int vb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int32_t rows, int32_t cols, float eps, vb_stream_t stream);
+/* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta accumulated (+=) into f32 [cols] when non-NULL.
+ * `partial` is a caller workspace of vb_layernorm_bwd_workspace_bytes(cols) bytes. */
+int64_t vb_layernorm_bwd_workspace_bytes(int32_t cols);
+int vb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, void* partial, int32_t rows,
+                     int32_t cols, vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention core (architecture.py:212-233): softmax(q k^T / sqrt(d)) v, non-causal, no dropout.
+ * qkv: bf16 [batch*seq, 3*E] as produced by the fused qkv Linear (column = which*E + head*d + j);
+ * out: bf16 [batch*seq, E] (heads merged); lse: f32 [batch, heads, seq] (log-sum-exp of scaled scores).
+ * head_dim must be 64.
+ * ------------------------------------------------------------------------------------------------ */
+int vb_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t seq, int32_t heads,
+                     int32_t head_dim, vb_stream_t stream);
+/* dqkv: bf16 [batch*seq, 3*E]; dout: bf16 [batch*seq, E] */
+int vb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                     int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
+/* Paired attention for the plasticity estimator: runs the core on qkv_a and qkv_b (same shapes) and writes
+ * delta = attn(qkv_a) - attn(qkv_b), subtracted in fp32 before the bf16 down-cast. */
+int vb_attention_pair_delta(const void* qkv_a, const void* qkv_b, int64_t ld_qkv, void* delta, int64_t ld_delta,
+                            int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Element-wise / data-movement helpers on the path
+ * ------------------------------------------------------------------------------------------------ */
+/* f32 -> bf16 over n elements (weights shadow copy; activations at the module boundary) */
+int vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vb_stream_t stream);
+int vb_cast_bf16_to_f32(const void* src, float* dst, int64_t n, vb_stream_t stream);
+/* im2col for non-overlapping P x P patches (transformer/utils.py:91,114): img f32 [N,C,H,W] ->
+ * patches bf16 [N*(H/P)*(W/P), C*P*P], column = c*P*P + py*P + px. If img2 != NULL, writes img - img2
+ * (subtracted in fp32). */
+int vb_im2col_patches(const float* img, const float* img2, void* patches, int32_t n, int32_t c, int32_t h,
+                      int32_t w, int32_t p, vb_stream_t stream);
+/* tokens[b, 0, :] = cls + pos[0]; tokens[b, 1+i, :] = patch_out[b*np + i, :] + pos[1+i]
+ * (architecture.py:666-675). patch_out bf16 [batch*np, E] -> tokens bf16 [batch*(np+1), E];
+ * tokens_f32 (optional, may be NULL) receives the same values before the bf16 rounding. */
+int vb_assemble_tokens(const void* patch_out, const float* patch_out_f32, const float* cls, const float* pos,
+                       void* tokens, float* tokens_f32, int32_t batch, int32_t np, int32_t e, vb_stream_t stream);
+/* backward of the above: dpatch_out (bf16 [batch*np, E]) = dtokens rows 1..np; dcls += sum_b dtokens[b,0];
+ * dpos += sum_b dtokens[b]. dcls/dpos may be NULL (frozen embedding). */
+int vb_assemble_tokens_bwd(const void* dtokens, void* dpatch_out, float* dcls, float* dpos, int32_t batch,
+                           int32_t np, int32_t e, vb_stream_t stream);
+/* out[c] += sum_r x[r, c]  (bias gradients). x bf16 [rows, cols] with row stride ldx. */
+int vb_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t rows, int32_t cols, vb_stream_t stream);
+/* y = a + b (bf16), n elements */
+int vb_add_bf16(const void* a, const void* b, void* y, int64_t n, vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Plasticity reductions (apps/vit/analysis.py:68 `distance`; apps/plots/analysis.py:97 ratio)
+ * ------------------------------------------------------------------------------------------------ */
+/* out[s] += sum over the sample's rows/cols of (a - b)^2, a/b f32 [n_samples*rows_per_sample, cols];
+ * b may be NULL (then a is already a difference). */
+int vb_rowsumsq_diff_f32(const float* a, const float* b, float* out, int32_t n_samples, int32_t rows_per_sample,
+                         int32_t cols, vb_stream_t stream);
+/* LayerNorm plasticity for all norms at once: u[s, d] = sum_l (zhat_a[s,l,d] - zhat_b[s,l,d])^2 where zhat is
+ * the normalised (no affine) row; the per-norm squared distance is then sum_d gamma[d]^2 u[s,d]
+ * (LN_i(a) - LN_i(b) = gamma_i * (zhat_a - zhat_b); beta cancels). a, b: f32 [n_samples*rows, cols]. */
+int vb_layernorm_pair_sqdiff(const float* a, const float* b, float* u, int32_t n_samples, int32_t rows_per_sample,
+                             int32_t cols, float eps, vb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITB200_H */

@@ -1,0 +1,326 @@
+"""Kernel-level parity: every C-ABI entry point against a plain PyTorch fp32 reference of the same op.
+
+Tolerances (stated per test): inputs are bf16, accumulation is fp32 on both sides, so GEMM-type outputs must agree
+to bf16 output rounding (rel 2^-8) plus summation-order noise; fp32 outputs to ~1e-5 relative.
+"""
+
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _lib():
+    from vit_plasticity_b200 import _lib
+
+    return _lib
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _report(name, got, ref, atol, rtol):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    if bad.any():
+        idx = torch.nonzero(bad)
+        rows = idx[:, 0]
+        cols = idx[:, 1] if idx.shape[1] > 1 else idx[:, 0]
+        msg = (
+            f"{name}: {int(bad.sum())}/{bad.numel()} mismatches, max abs err {float(err.max()):.4g} "
+            f"(ref max {float(ref.abs().max()):.4g}); first bad at {idx[0].tolist()} got {float(got[tuple(idx[0])]):.5g} "
+            f"ref {float(ref[tuple(idx[0])]):.5g}; bad rows range [{int(rows.min())},{int(rows.max())}] "
+            f"cols range [{int(cols.min())},{int(cols.max())}]"
+        )
+        if got.dim() == 2:
+            # coarse 32x32 block map of the failures (first 16x16 blocks)
+            bm = bad[: 32 * 16, : 32 * 16]
+            pr, pc = (-bm.shape[0]) % 32, (-bm.shape[1]) % 32
+            bm = torch.nn.functional.pad(bm, (0, pc, 0, pr))
+            blk = bm.reshape(bm.shape[0] // 32, 32, bm.shape[1] // 32, 32).any(3).any(1)
+            msg += "\nblock map (32x32):\n" + "\n".join("".join("X" if v else "." for v in r) for r in blk.tolist())
+        pytest.fail(msg)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [(128, 256, 64), (256, 256, 128), (384, 512, 256), (1000, 768, 768), (197 * 3, 2304, 768), (130, 136, 72)]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_gemm_kmajor_bias(m, n, k):
+    L = _lib()
+    a = _rand(m, k, seed=1).bfloat16()
+    b = _rand(n, k, seed=2, scale=0.05).bfloat16()
+    bias = _rand(n, seed=3)
+    out = torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16)
+    L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_BF16, bias=bias, out=out)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().T + bias
+    _report("gemm_bias", out, ref, atol=2e-2, rtol=1e-2)
+
+
+def test_gemm_nobias_f32_out():
+    L = _lib()
+    m, n, k = 300, 512, 320
+    a = _rand(m, k, seed=1).bfloat16()
+    b = _rand(n, k, seed=2, scale=0.05).bfloat16()
+    out = torch.full((m, n), float("nan"), device=DEV, dtype=torch.float32)
+    L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_F32, out=out)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().T
+    _report("gemm_f32", out, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_gemm_residual():
+    L = _lib()
+    m, n, k = 788, 768, 3072
+    a = _rand(m, k, seed=1).bfloat16()
+    b = _rand(n, k, seed=2, scale=0.02).bfloat16()
+    bias = _rand(n, seed=3)
+    res = _rand(m, n, seed=4).bfloat16()
+    out = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_BF16_RESID, bias=bias, aux=res, out=out)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().T + bias + res.float()
+    _report("gemm_resid", out, ref, atol=3e-2, rtol=1e-2)
+
+
+def test_gemm_gelu_two_outputs():
+    L = _lib()
+    m, n, k = 394, 3072, 768
+    a = _rand(m, k, seed=1).bfloat16()
+    b = _rand(n, k, seed=2, scale=0.05).bfloat16()
+    bias = _rand(n, seed=3)
+    act = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    z = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_BF16_GELU, bias=bias, out=act, out2=z)
+    torch.cuda.synchronize()
+    zref = a.float() @ b.float().T + bias
+    _report("gemm_gelu.z", z, zref, atol=2e-2, rtol=1e-2)
+    # activation must be gelu of the *stored* (bf16-rounded) pre-activation
+    _report("gemm_gelu.a", act, torch.nn.functional.gelu(z.float()), atol=1e-3, rtol=1e-2)
+
+
+def test_gemm_dgrad_mn_major_b_with_dgelu():
+    L = _lib()
+    tokens, n_out, k_in = 394, 768, 3072  # dx[tokens, k_in] = dy[tokens, n_out] @ W[n_out, k_in]
+    dy = _rand(tokens, n_out, seed=1).bfloat16()
+    w = _rand(n_out, k_in, seed=2, scale=0.05).bfloat16()
+    z = _rand(tokens, k_in, seed=3).bfloat16()
+    out = torch.empty(tokens, k_in, device=DEV, dtype=torch.bfloat16)
+    L.gemm(dy, w, m=tokens, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16, out=out)
+    torch.cuda.synchronize()
+    ref = dy.float() @ w.float()
+    _report("dgrad", out, ref, atol=3e-2, rtol=1e-2)
+    L.gemm(dy, w, m=tokens, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_DGELU, aux=z, out=out)
+    torch.cuda.synchronize()
+    zf = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).backward(ref)
+    _report("dgrad_dgelu", out, zf.grad, atol=3e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("tokens,n_out,k_in,split_k", [(256, 128, 256, 1), (1000, 768, 768, 3), (197 * 8, 2304, 768, 4), (333, 136, 200, 2)])
+def test_gemm_wgrad_mn_major_both_splitk(tokens, n_out, k_in, split_k):
+    L = _lib()
+    dy = _rand(tokens, n_out, seed=1).bfloat16()
+    x = _rand(tokens, k_in, seed=2).bfloat16()
+    dw = torch.zeros(n_out, k_in, device=DEV, dtype=torch.float32)
+    L.gemm(dy, x, m=n_out, n=k_in, k=tokens, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=split_k)
+    torch.cuda.synchronize()
+    ref = dy.float().T @ x.float()
+    _report("wgrad", dw, ref, atol=2e-3, rtol=1e-4)
+    # accumulate semantics: a second call doubles the result
+    L.gemm(dy, x, m=n_out, n=k_in, k=tokens, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=split_k)
+    torch.cuda.synchronize()
+    _report("wgrad_acc", dw, 2 * ref, atol=4e-3, rtol=1e-4)
+
+
+def test_gemm_sumsq_per_sample_group():
+    L = _lib()
+    samples, rows, k, n, cpg = 6, 197, 768, 1536, 768
+    m = samples * rows
+    a = _rand(m, k, seed=1).bfloat16()
+    b = _rand(n, k, seed=2, scale=0.05).bfloat16()
+    ss = torch.zeros(samples, n // cpg, device=DEV, dtype=torch.float32)
+    L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_SUMSQ, sumsq=ss, rows_per_sample=rows, cols_per_group=cpg, n_groups=n // cpg)
+    torch.cuda.synchronize()
+    c = (a.float() @ b.float().T).reshape(samples, rows, n // cpg, cpg)
+    ref = (c**2).sum(dim=(1, 3))
+    _report("sumsq", ss, ref, atol=1e-2, rtol=1e-4)
+
+
+def test_gemm_strided_a_view():
+    L = _lib()
+    m, n, k = 256, 256, 128
+    big = _rand(m, 3 * k, seed=1).bfloat16()
+    a = big[:, k : 2 * k]
+    b = _rand(n, k, seed=2, scale=0.05).bfloat16()
+    out = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    L.gemm(a, b, m=m, n=n, k=k, out=out)
+    torch.cuda.synchronize()
+    _report("gemm_strided", out, a.float() @ b.float().T, atol=2e-2, rtol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# LayerNorm
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols", [(197 * 4, 768), (100, 1024), (37, 128), (64, 1280)])
+def test_layernorm_fwd_bwd(rows, cols):
+    L = _lib()
+    eps = 1e-12
+    x = (_rand(rows, cols, seed=1) * 2 + 0.5).bfloat16()
+    g = _rand(cols, seed=2) * 0.5 + 1.0
+    b = _rand(cols, seed=3) * 0.1
+    y, mean, rstd = L.layernorm_fwd(x, g, b, eps)
+    torch.cuda.synchronize()
+    xf = x.float().requires_grad_(True)
+    gf = g.clone().requires_grad_(True)
+    bf = b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xf, (cols,), gf, bf, eps)
+    _report("ln_fwd", y, ref, atol=2e-2, rtol=1e-2)
+    _report("ln_mean", mean[:, None], xf.mean(1, keepdim=True), atol=1e-5, rtol=1e-5)
+    dy = _rand(rows, cols, seed=4).bfloat16()
+    dres = _rand(rows, cols, seed=5).bfloat16()
+    ref.backward(dy.float())
+    dg = torch.zeros(cols, device=DEV)
+    db = torch.zeros(cols, device=DEV)
+    dx = L.layernorm_bwd(dy, x, g, mean, rstd, dres=dres, dgamma=dg, dbeta=db)
+    torch.cuda.synchronize()
+    _report("ln_dx", dx, xf.grad + dres.float(), atol=3e-2, rtol=1e-2)
+    _report("ln_dgamma", dg[None], gf.grad[None], atol=1e-2, rtol=1e-3)
+    _report("ln_dbeta", db[None], bf.grad[None], atol=1e-2, rtol=1e-3)
+
+
+def test_layernorm_constant_row_is_finite():
+    L = _lib()
+    x = torch.full((8, 768), 3.0, device=DEV, dtype=torch.bfloat16)
+    g = torch.ones(768, device=DEV)
+    b = torch.full((768,), 0.25, device=DEV)
+    y, _, rstd = L.layernorm_fwd(x, g, b, 1e-12)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all() and torch.isfinite(rstd).all()
+    assert torch.allclose(y.float(), torch.full_like(y.float(), 0.25))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Attention
+# ---------------------------------------------------------------------------------------------------
+def _attn_ref(qkv, batch, seq, heads, hd):
+    e = heads * hd
+    q, k, v = qkv.float().reshape(batch, seq, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    p = torch.softmax(s, dim=-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(batch * seq, e)
+    return o, torch.logsumexp(s, dim=-1)
+
+
+@pytest.mark.parametrize("batch,seq,heads", [(2, 197, 12), (3, 5, 2), (1, 17, 4), (2, 208, 3), (1, 257, 2)])
+def test_attention_fwd_bwd(batch, seq, heads):
+    L = _lib()
+    hd = 64
+    e = heads * hd
+    qkv = _rand(batch * seq, 3 * e, seed=1).bfloat16()
+    out, lse = L.attention_fwd(qkv, batch, seq, heads, hd)
+    torch.cuda.synchronize()
+    qf = qkv.float().requires_grad_(True)
+    oref, lref = _attn_ref(qf, batch, seq, heads, hd)
+    _report("attn_out", out, oref, atol=2e-2, rtol=2e-2)
+    _report("attn_lse", lse.reshape(-1, seq), lref.reshape(-1, seq), atol=2e-3, rtol=1e-3)
+    dout = _rand(batch * seq, e, seed=2).bfloat16()
+    oref.backward(dout.float())
+    dqkv = L.attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd)
+    torch.cuda.synchronize()
+    _report("attn_dqkv", dqkv, qf.grad, atol=3e-2, rtol=3e-2)
+
+
+def test_attention_pair_delta():
+    L = _lib()
+    batch, seq, heads, hd = 2, 197, 12, 64
+    e = heads * hd
+    qa = _rand(batch * seq, 3 * e, seed=1).bfloat16()
+    qb = _rand(batch * seq, 3 * e, seed=2).bfloat16()
+    delta = torch.empty(batch * seq, e, device=DEV, dtype=torch.bfloat16)
+    L.attention_pair_delta(qa, qb, delta, batch, seq, heads, hd)
+    torch.cuda.synchronize()
+    ref = _attn_ref(qa, batch, seq, heads, hd)[0] - _attn_ref(qb, batch, seq, heads, hd)[0]
+    _report("attn_pair", delta, ref, atol=2e-2, rtol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Element-wise helpers
+# ---------------------------------------------------------------------------------------------------
+def test_casts_roundtrip():
+    L = _lib()
+    x = _rand(1000003 // 1, seed=1)[: 1000000 - 3].contiguous()
+    xb = L.cast_f32_to_bf16(x)
+    assert torch.equal(xb, x.bfloat16())
+    assert torch.equal(L.cast_bf16_to_f32(xb), xb.float())
+
+
+def test_im2col_matches_conv_unfold():
+    L = _lib()
+    n, c, h, w, p = 3, 3, 64, 48, 16
+    img = _rand(n, c, h, w, seed=1)
+    img2 = _rand(n, c, h, w, seed=2)
+    ref = torch.nn.functional.unfold(img, kernel_size=p, stride=p).transpose(1, 2).reshape(-1, c * p * p)
+    assert torch.equal(L.im2col_patches(img, p), ref.bfloat16())
+    ref2 = torch.nn.functional.unfold(img - img2, kernel_size=p, stride=p).transpose(1, 2).reshape(-1, c * p * p)
+    assert torch.equal(L.im2col_patches(img, p, img2), ref2.bfloat16())
+
+
+def test_assemble_tokens_fwd_bwd():
+    L = _lib()
+    batch, np_, e = 5, 196, 768
+    po = _rand(batch * np_, e, seed=1).bfloat16()
+    cls = _rand(e, seed=2)
+    pos = _rand(np_ + 1, e, seed=3)
+    tok, tok32 = L.assemble_tokens(po, None, cls, pos, batch, np_, e, want_f32=True)
+    ref = torch.cat([cls.expand(batch, 1, e), po.float().reshape(batch, np_, e)], 1) + pos
+    assert torch.allclose(tok32.reshape(batch, np_ + 1, e), ref, atol=1e-6)
+    assert torch.equal(tok, ref.reshape(-1, e).bfloat16())
+    dtok = _rand(batch * (np_ + 1), e, seed=4).bfloat16()
+    dcls = torch.zeros(e, device=DEV)
+    dpos = torch.zeros(np_ + 1, e, device=DEV)
+    dpatch = L.assemble_tokens_bwd(dtok, dcls, dpos, batch, np_, e)
+    d3 = dtok.float().reshape(batch, np_ + 1, e)
+    assert torch.equal(dpatch.reshape(batch, np_, e), dtok.reshape(batch, np_ + 1, e)[:, 1:])
+    assert torch.allclose(dpos, d3.sum(0), atol=1e-4)
+    assert torch.allclose(dcls, d3[:, 0].sum(0), atol=1e-4)
+
+
+def test_colsum_and_add():
+    L = _lib()
+    x = _rand(1234, 2304, seed=1).bfloat16()
+    out = torch.ones(2304, device=DEV)
+    L.colsum_bf16(x, out)
+    assert torch.allclose(out, 1 + x.float().sum(0), atol=2e-2, rtol=1e-4)
+    y = _rand(1234, 2304, seed=2).bfloat16()
+    assert torch.equal(L.add_bf16(x, y), (x.float() + y.float()).bfloat16())
+
+
+def test_rowsumsq_and_ln_pair():
+    L = _lib()
+    s, rows, cols = 4, 197, 768
+    a = _rand(s * rows, cols, seed=1)
+    b = _rand(s * rows, cols, seed=2)
+    out = torch.zeros(s, device=DEV)
+    L.rowsumsq_diff_f32(a, b, out, s, rows, cols)
+    ref = ((a - b) ** 2).reshape(s, -1).sum(1)
+    assert torch.allclose(out, ref, rtol=1e-5)
+    u = torch.zeros(s, cols, device=DEV)
+    L.layernorm_pair_sqdiff(a, b, u, s, rows, cols, 1e-12)
+    za = torch.nn.functional.layer_norm(a, (cols,), eps=1e-12)
+    zb = torch.nn.functional.layer_norm(b, (cols,), eps=1e-12)
+    refu = ((za - zb) ** 2).reshape(s, rows, cols).sum(1)
+    assert torch.allclose(u, refu, rtol=1e-4, atol=1e-4)

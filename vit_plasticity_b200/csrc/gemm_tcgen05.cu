@@ -1,0 +1,474 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring -> tcgen05.mma (128x256x16, cta_group::1)
+//   -> double-buffered fp32 accumulators in TMEM (2 x 256 columns) -> tcgen05.ld epilogue on 8 warps
+//   -> swizzled smem staging -> TMA store / TMA reduce-add.
+//
+// One kernel serves every dense contraction of the ViT hot path:
+//   forward  y  = x W^T (+bias, +GELU, +residual)     A K-major,  B K-major
+//   dgrad    dx = dy W  (x gelu'(z))                  A K-major,  B MN-major (weights used as stored)
+//   wgrad    dW += dy^T x  (split-K, TMA reduce-add)  A MN-major, B MN-major (activations used as stored)
+//   plasticity: sum of squares of the accumulator per sample, nothing written back
+//
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
+// warps 4..11 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the 128-column half of the tile).
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_FIRST_WARP = 4;
+constexpr int STAGING_BYTES = 4096;  // per epilogue warp: 2 x (32 rows x 64 B) bf16 or 1 x (32 rows x 128 B) f32
+constexpr int GEMM_THREADS = (EPI_FIRST_WARP + EPI_WARPS) * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES + 256 + 1024;  // + barriers + align
+
+struct GemmKernelParams {
+    int M, N, K;
+    int num_m_blocks, num_n_blocks, num_k_blocks;
+    int split_k, kb_per_split;
+    int epi;
+    const float* bias;
+    const bf16* aux;
+    long long ld_aux;
+    float* sumsq;
+    int rows_per_sample, cols_per_group, n_groups;
+};
+
+struct WorkItem {
+    int m_blk, n_blk, kb0, kb1;
+};
+
+__device__ __forceinline__ WorkItem decode_work(const GemmKernelParams& p, int w) {
+    // split index is the slowest so that concurrently running CTAs share the same K-slice (L2 reuse in wgrad);
+    // within a split, n is fastest so CTAs running together share the A row panel.
+    int tiles = p.num_m_blocks * p.num_n_blocks;
+    int split = w / tiles;
+    int tile = w - split * tiles;
+    WorkItem it;
+    it.m_blk = tile / p.num_n_blocks;
+    it.n_blk = tile - it.m_blk * p.num_n_blocks;
+    it.kb0 = split * p.kb_per_split;
+    it.kb1 = min(it.kb0 + p.kb_per_split, p.num_k_blocks);
+    return it;
+}
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                    const GemmKernelParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte aligned stage buffers
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* staging_base = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + EPI_WARPS * STAGING_BYTES);
+    uint64_t* full_bar = bars;                   // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;         // [STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]     epilogue -> MMA
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        tma_prefetch_desc(&tmC2);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int total_work = p.num_m_blocks * p.num_n_blocks * p.split_k;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const WorkItem it = decode_work(p, w);
+                for (int kb = it.kb0; kb < it.kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    if (A_MN == 0) {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, it.m_blk * BM);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            tma_load_2d(sa + i * (64 * BK * 2), &tmA, &full_bar[stage], it.m_blk * BM + i * 64, kb * BK);
+                    }
+                    if (B_MN == 0) {
+                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, it.n_blk * BN);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            tma_load_2d(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], it.n_blk * BN + i * 64, kb * BK);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const WorkItem it = decode_work(p, w);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = it.kb0; kb < it.kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // K-major : 8-row groups 1024 B apart (SBO), step 16 elements = 32 B inside the swizzle span
+                        // MN-major: 64-element MN chunks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO),
+                        //           step 16 k-rows = 2048 B
+                        const uint64_t adesc = A_MN == 0 ? make_smem_desc_sw128(sa + k * 32, 16, 1024)
+                                                         : make_smem_desc_sw128(sa + k * 2048, 64 * BK * 2, 1024);
+                        const uint64_t bdesc = B_MN == 0 ? make_smem_desc_sw128(sb + k * 32, 16, 1024)
+                                                         : make_smem_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024);
+                        umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull_bar[acc]);  // accumulator complete
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= EPI_FIRST_WARP) {
+        // =========================== epilogue ===========================
+        const int ew = warp - EPI_FIRST_WARP;
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int hf = ew >> 2;   // which 128-column half of the tile
+        uint8_t* stg = staging_base + ew * STAGING_BYTES;
+        const int epi = p.epi;
+        const bool has_aux = (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int buf = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const WorkItem it = decode_work(p, w);
+            const int row0 = it.m_blk * BM + q * 32;
+            const int row = row0 + lane;
+            const int colbase = it.n_blk * BN + hf * 128;
+            const bool row_ok = row < p.M;
+
+            uint4 aux_cur[4], aux_nxt[4];
+            auto load_aux = [&](uint4(&dst)[4], int col0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(0, 0, 0, 0);
+                if (has_aux && row_ok) {
+                    const bf16* src = p.aux + (long long)row * p.ld_aux + col0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col0 + j * 8 < p.N) dst[j] = __ldg(reinterpret_cast<const uint4*>(src) + j);
+                }
+            };
+            load_aux(aux_cur, colbase);  // issued before the accumulator wait: latency hides behind the MMA
+
+            mbar_wait(&tfull_bar[acc], acc_phase, 4);
+            tc_fence_after();
+
+            float sumsq_local = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = colbase + c * 32;
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + hf * 128 + c * 32, v);
+                if (c < 3) load_aux(aux_nxt, col0 + 32);
+                tmem_ld_wait();
+                if (col0 < p.N) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias != nullptr && epi != VB_EPI_F32_ADD && epi != VB_EPI_SUMSQ && epi != VB_EPI_BF16_DGELU) {
+                        if (col0 + 32 <= p.N) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                                f[4 * j + 0] += b4.x;
+                                f[4 * j + 1] += b4.y;
+                                f[4 * j + 2] += b4.z;
+                                f[4 * j + 3] += b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+                        }
+                    }
+                    if (epi == VB_EPI_SUMSQ) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) sumsq_local += f[j] * f[j];
+                    } else if (epi == VB_EPI_F32 || epi == VB_EPI_F32_ADD) {
+                        // 32 rows x 128 B, 16-byte chunk index XOR (row & 7) == TMA SWIZZLE_128B
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+                        const uint32_t rowaddr = smem_u32(stg) + lane * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t a = rowaddr + ((j ^ (lane & 7)) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(f[4 * j]),
+                                         "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                                         : "memory");
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (epi == VB_EPI_F32)
+                                tma_store_2d(&tmC, stg, col0, row0);
+                            else
+                                tma_reduce_add_2d(&tmC, stg, col0, row0);
+                            tma_store_commit();
+                        }
+                    } else {
+                        // bf16 outputs: 32 rows x 64 B, chunk index XOR ((row >> 1) & 3) == TMA SWIZZLE_64B
+                        uint32_t o[16], o2[16];
+                        if (epi == VB_EPI_BF16_RESID) {
+                            const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 r = unpack_bf16x2(ax[j]);
+                                o[j] = pack_bf16x2(f[2 * j] + r.x, f[2 * j + 1] + r.y);
+                            }
+                        } else if (epi == VB_EPI_BF16_DGELU) {
+                            const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 z = unpack_bf16x2(ax[j]);
+                                o[j] = pack_bf16x2(f[2 * j] * dgelu_erf(z.x), f[2 * j + 1] * dgelu_erf(z.y));
+                            }
+                        } else if (epi == VB_EPI_BF16_GELU) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                // GELU is applied to the bf16-rounded pre-activation so that forward and the
+                                // saved z used by backward agree exactly
+                                const uint32_t zz = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                                const float2 z = unpack_bf16x2(zz);
+                                o2[j] = zz;
+                                o[j] = pack_bf16x2(gelu_erf(z.x), gelu_erf(z.y));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                        }
+                        const bool two = (epi == VB_EPI_BF16_GELU);
+                        uint8_t* b0 = stg + (two ? 0 : buf * 2048);
+                        if (lane == 0) {
+                            if (two)
+                                tma_store_wait_read<0>();
+                            else
+                                tma_store_wait_read<1>();
+                        }
+                        __syncwarp();
+                        const uint32_t rowaddr = smem_u32(b0) + lane * 64;
+                        const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t a = rowaddr + ((j ^ sw) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o[4 * j]),
+                                         "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3])
+                                         : "memory");
+                            if (two)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(o2[4 * j]),
+                                             "r"(o2[4 * j + 1]), "r"(o2[4 * j + 2]), "r"(o2[4 * j + 3])
+                                             : "memory");
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC, b0, col0, row0);
+                            if (two) tma_store_2d(&tmC2, b0 + 2048, col0, row0);
+                            tma_store_commit();
+                        }
+                        buf ^= 1;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) aux_cur[j] = aux_nxt[j];
+            }
+            // all tcgen05.ld of this accumulator have completed (wait::ld above): hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+
+            if (epi == VB_EPI_SUMSQ && colbase < p.N) {
+                const int group = colbase / p.cols_per_group;
+                const int sample = row_ok ? row / p.rows_per_sample : -1;
+                const int s0 = __shfl_sync(0xffffffffu, sample, 0);
+                const bool uniform = __all_sync(0xffffffffu, sample == s0);
+                if (uniform) {
+                    const float t = warp_sum(sumsq_local);
+                    if (lane == 0 && s0 >= 0) atomicAdd(p.sumsq + (long long)s0 * p.n_groups + group, t);
+                } else if (row_ok) {
+                    atomicAdd(p.sumsq + (long long)sample * p.n_groups + group, sumsq_local);
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int A_MN, int B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+                       const GemmKernelParams& p, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    VB_CHECK_CUDA(cudaGetDevice(&dev));
+    auto kern = gemm_tcgen05_kernel<A_MN, B_MN>;
+    if (dev < 64 && !attr_set[dev]) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        attr_set[dev] = true;
+    }
+    const int total_work = p.num_m_blocks * p.num_n_blocks * p.split_k;
+    const int grid = total_work < num_sms() ? total_work : num_sms();
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+}  // namespace vb
+
+extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
+    using namespace vb;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(a != nullptr, "vb_gemm_bf16: null args");
+    VB_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "vb_gemm_bf16: bad shape m=%d n=%d k=%d", a->m, a->n, a->k);
+    VB_CHECK_ARG(a->a && a->b, "vb_gemm_bf16: null operand");
+    VB_CHECK_ARG(a->a_layout == 0 || a->a_layout == 1, "vb_gemm_bf16: bad a_layout %d", a->a_layout);
+    VB_CHECK_ARG(a->b_layout == 0 || a->b_layout == 1, "vb_gemm_bf16: bad b_layout %d", a->b_layout);
+    VB_CHECK_ARG(a->epilogue >= VB_EPI_BF16 && a->epilogue <= VB_EPI_SUMSQ, "vb_gemm_bf16: bad epilogue %d",
+                 a->epilogue);
+    VB_CHECK_ARG(a->n % 8 == 0, "vb_gemm_bf16: n=%d must be a multiple of 8", a->n);
+    const int epi = a->epilogue;
+    const int split_k = a->split_k < 1 ? 1 : a->split_k;
+    VB_CHECK_ARG(split_k == 1 || epi == VB_EPI_F32_ADD, "vb_gemm_bf16: split_k > 1 needs VB_EPI_F32_ADD");
+    if (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU)
+        VB_CHECK_ARG(a->aux != nullptr && a->ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,
+                     "vb_gemm_bf16: aux must be non-null, 16B aligned, ld multiple of 8");
+    if (epi == VB_EPI_SUMSQ)
+        VB_CHECK_ARG(a->sumsq && a->rows_per_sample > 0 && a->cols_per_group > 0 && a->cols_per_group % 128 == 0 &&
+                         a->n_groups > 0,
+                     "vb_gemm_bf16: SUMSQ needs sumsq, rows_per_sample, cols_per_group %% 128 == 0, n_groups");
+    else
+        VB_CHECK_ARG(a->out != nullptr, "vb_gemm_bf16: null out");
+    if (epi == VB_EPI_BF16_GELU) VB_CHECK_ARG(a->out2 != nullptr, "vb_gemm_bf16: GELU epilogue needs out2");
+    if (a->bias) VB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "vb_gemm_bf16: bias must be 16B aligned");
+
+    CUtensorMap tmA, tmB, tmC, tmC2;
+    int rc;
+    if (a->a_layout == 0)
+        rc = make_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->a, a->k, a->m, a->lda * 2, BK, BM,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    else
+        rc = make_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->a, a->m, a->k, a->lda * 2, 64, BK,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (a->b_layout == 0)
+        rc = make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, a->k, a->n, a->ldb * 2, BK, BN,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    else
+        rc = make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, a->n, a->k, a->ldb * 2, 64, BK,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (epi == VB_EPI_SUMSQ) {
+        tmC = tmA;  // unused
+        tmC2 = tmA;
+    } else if (epi == VB_EPI_F32 || epi == VB_EPI_F32_ADD) {
+        rc = make_tensor_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, a->n, a->m, a->ld_out * 4, 32, 32,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        tmC2 = tmC;
+    } else {
+        rc = make_tensor_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->out, a->n, a->m, a->ld_out * 2, 32, 32,
+                                CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        if (epi == VB_EPI_BF16_GELU) {
+            rc = make_tensor_map_2d(&tmC2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->out2, a->n, a->m, a->ld_out2 * 2, 32,
+                                    32, CU_TENSOR_MAP_SWIZZLE_64B);
+            if (rc) return rc;
+        } else {
+            tmC2 = tmC;
+        }
+    }
+
+    GemmKernelParams p;
+    p.M = a->m;
+    p.N = a->n;
+    p.K = a->k;
+    p.num_m_blocks = (a->m + BM - 1) / BM;
+    p.num_n_blocks = (a->n + BN - 1) / BN;
+    p.num_k_blocks = (a->k + BK - 1) / BK;
+    int sk = split_k > p.num_k_blocks ? p.num_k_blocks : split_k;
+    p.kb_per_split = (p.num_k_blocks + sk - 1) / sk;
+    p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // every split is non-empty
+    p.epi = epi;
+    p.bias = a->bias;
+    p.aux = static_cast<const bf16*>(a->aux);
+    p.ld_aux = a->ld_aux;
+    p.sumsq = a->sumsq;
+    p.rows_per_sample = a->rows_per_sample;
+    p.cols_per_group = a->cols_per_group;
+    p.n_groups = a->n_groups;
+
+    if (a->a_layout == 0 && a->b_layout == 0) return launch_gemm<0, 0>(tmA, tmB, tmC, tmC2, p, stream);
+    if (a->a_layout == 0 && a->b_layout == 1) return launch_gemm<0, 1>(tmA, tmB, tmC, tmC2, p, stream);
+    if (a->a_layout == 1 && a->b_layout == 1) return launch_gemm<1, 1>(tmA, tmB, tmC, tmC2, p, stream);
+    return launch_gemm<1, 0>(tmA, tmB, tmC, tmC2, p, stream);
+}

@@ -1,0 +1,331 @@
+// Warp-per-row LayerNorm forward / backward (HBM-bound).
+//   - 128-bit loads/stores (8 bf16 per access), the whole row lives in registers, fp32 statistics
+//   - forward saves mean / rstd; backward fuses the residual-gradient add (dx = dres + LN'(dy)) and accumulates
+//     dgamma / dbeta in registers across a persistent row loop, one atomicAdd per column per block at the end.
+// Replaces nn.LayerNorm (reference: src/vitef/models/transformer/utils.py:293; call sites
+// architecture.py:347,349 and transformer/utils.py:396) and native_layer_norm_backward under autograd.
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+constexpr int LN_WARPS = 8;
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int cols,
+                     float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * LN_WARPS + warp;
+    if (row >= rows) return;
+    const int nchunks = cols >> 3;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * cols);
+    float v[CHUNKS][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            const uint4 u = __ldg(xr + c);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(w[j]);
+                v[i][2 * j] = f.x;
+                v[i][2 * j + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+        }
+    }
+    const float mean = warp_sum(sum) / (float)cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = v[i][j] - mean;
+                sq += d * d;
+            }
+        }
+    }
+    const float var = warp_sum(sq) / (float)cols;  // biased variance, as torch
+    const float rstd = rsqrtf(var + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+    uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * cols);
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+            uint4 u;
+            u.x = pack_bf16x2(o[0], o[1]);
+            u.y = pack_bf16x2(o[2], o[3]);
+            u.z = pack_bf16x2(o[4], o[5]);
+            u.w = pack_bf16x2(o[6], o[7]);
+            yr[c] = u;
+        }
+    }
+}
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
+                     bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols) {
+    __shared__ float red[LN_WARPS][32 * 8 + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = cols >> 3;
+    float dg[CHUNKS][8], db[CHUNKS][8], g[CHUNKS][8];
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+        const int c = lane + i * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dg[i][j] = 0.f;
+            db[i][j] = 0.f;
+            g[i][j] = (c < nchunks) ? __ldg(gamma + c * 8 + j) : 0.f;
+        }
+    }
+    const float inv_cols = 1.f / (float)cols;
+    for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * cols);
+        const uint4* dyr = reinterpret_cast<const uint4*>(dy + (size_t)row * cols);
+        const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+        float xh[CHUNKS][8], gy[CHUNKS][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+                const uint4 ux = __ldg(xr + c), ud = __ldg(dyr + c);
+                const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w};
+                const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 fx = unpack_bf16x2(wx[j]);
+                    const float2 fd = unpack_bf16x2(wd[j]);
+                    const float h0 = (fx.x - mu) * rs, h1 = (fx.y - mu) * rs;
+                    xh[i][2 * j] = h0;
+                    xh[i][2 * j + 1] = h1;
+                    dg[i][2 * j] += fd.x * h0;
+                    dg[i][2 * j + 1] += fd.y * h1;
+                    db[i][2 * j] += fd.x;
+                    db[i][2 * j + 1] += fd.y;
+                    const float g0 = fd.x * g[i][2 * j], g1 = fd.y * g[i][2 * j + 1];
+                    gy[i][2 * j] = g0;
+                    gy[i][2 * j + 1] = g1;
+                    s1 += g0 + g1;
+                    s2 += g0 * h0 + g1 * h1;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] = 0.f;
+                    gy[i][j] = 0.f;
+                }
+            }
+        }
+        s1 = warp_sum(s1) * inv_cols;
+        s2 = warp_sum(s2) * inv_cols;
+        uint4* dxr = reinterpret_cast<uint4*>(dx + (size_t)row * cols);
+        const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + (size_t)row * cols) : nullptr;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rs * (gy[i][j] - s1 - xh[i][j] * s2);
+                if (drr) {
+                    const uint4 ur = __ldg(drr + c);
+                    const uint32_t wr[4] = {ur.x, ur.y, ur.z, ur.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 fr = unpack_bf16x2(wr[j]);
+                        o[2 * j] += fr.x;
+                        o[2 * j + 1] += fr.y;
+                    }
+                }
+                uint4 u;
+                u.x = pack_bf16x2(o[0], o[1]);
+                u.y = pack_bf16x2(o[2], o[3]);
+                u.z = pack_bf16x2(o[4], o[5]);
+                u.w = pack_bf16x2(o[6], o[7]);
+                dxr[c] = u;
+            }
+        }
+    }
+    if (dgamma == nullptr && dbeta == nullptr) return;  // frozen norm: parameter gradients not needed
+    // block reduction of the per-warp partials, one chunk-slot at a time, then one atomic per column
+    for (int pass = 0; pass < 2; ++pass) {
+        float* out = pass == 0 ? dgamma : dbeta;
+        if (out == nullptr) continue;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? dg[i][j] : db[i][j];
+            __syncthreads();
+            const int t = threadIdx.x;  // 256 threads <-> 256 columns of this slot
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < LN_WARPS; ++w) s += red[w][t];
+            const int col = (i * 32 + (t >> 3)) * 8 + (t & 7);
+            if (col < cols) atomicAdd(out + col, s);
+        }
+    }
+}
+
+// u[s, d] = sum_l (zhat_a - zhat_b)^2 ; one warp per (sample,row) pair of rows, f32 inputs
+template <int CHUNKS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_pair_sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ u,
+                             int n_samples, int rows_per_sample, int cols, float eps) {
+    // block = one sample; warps stride over the sample's rows; per-lane column accumulators
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x;
+    const int nchunks = cols >> 2;  // float4 chunks
+    float acc[CHUNKS][4];
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int r = blockIdx.y * LN_WARPS + warp; r < rows_per_sample; r += gridDim.y * LN_WARPS) {
+        const size_t row = (size_t)s * rows_per_sample + r;
+        const float4* ar = reinterpret_cast<const float4*>(a + row * cols);
+        const float4* br = reinterpret_cast<const float4*>(b + row * cols);
+        float va[CHUNKS][4], vb_[CHUNKS][4];
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+                const float4 fa = __ldg(ar + c), fb = __ldg(br + c);
+                va[i][0] = fa.x; va[i][1] = fa.y; va[i][2] = fa.z; va[i][3] = fa.w;
+                vb_[i][0] = fb.x; vb_[i][1] = fb.y; vb_[i][2] = fb.z; vb_[i][3] = fb.w;
+                sa += fa.x + fa.y + fa.z + fa.w;
+                sb += fb.x + fb.y + fb.z + fb.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { va[i][j] = 0.f; vb_[i][j] = 0.f; }
+            }
+        }
+        const float ma = warp_sum(sa) / (float)cols, mb = warp_sum(sb) / (float)cols;
+        float qa = 0.f, qb = 0.f;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float da = va[i][j] - ma, db = vb_[i][j] - mb;
+                    qa += da * da;
+                    qb += db * db;
+                }
+            }
+        }
+        const float ra = rsqrtf(warp_sum(qa) / (float)cols + eps), rb = rsqrtf(warp_sum(qb) / (float)cols + eps);
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = (va[i][j] - ma) * ra - (vb_[i][j] - mb) * rb;
+                    acc[i][j] += d * d;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(u + (size_t)s * cols + c * 4 + j, acc[i][j]);
+        }
+    }
+}
+
+}  // namespace vb
+
+#define VB_LN_DISPATCH(chunks, CALL)            \
+    switch (chunks) {                           \
+        case 1: { constexpr int C = 1; CALL; } break; \
+        case 2: { constexpr int C = 2; CALL; } break; \
+        case 3: { constexpr int C = 3; CALL; } break; \
+        case 4: { constexpr int C = 4; CALL; } break; \
+        case 5: { constexpr int C = 5; CALL; } break; \
+        case 6: { constexpr int C = 6; CALL; } break; \
+        case 7: { constexpr int C = 7; CALL; } break; \
+        default: { constexpr int C = 8; CALL; } break; \
+    }
+
+extern "C" int vb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                int32_t rows, int32_t cols, float eps, vb_stream_t stream_) {
+    using namespace vb;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(x && gamma && beta && y, "vb_layernorm_fwd: null pointer");
+    VB_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 2048, "vb_layernorm_fwd: cols=%d must be a multiple of 8, <= 2048", cols);
+    const int chunks = (cols / 8 + 31) / 32;
+    const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+    VB_LN_DISPATCH(chunks, (layernorm_fwd_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(
+                               static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y), mean, rstd, rows, cols, eps)));
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+extern "C" int64_t vb_layernorm_bwd_workspace_bytes(int32_t cols) {
+    (void)cols;
+    return 0;  // parameter gradients are reduced with atomics; no workspace needed in this version
+}
+
+extern "C" int vb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                const void* dres, void* dx, float* dgamma, float* dbeta, void* partial, int32_t rows,
+                                int32_t cols, vb_stream_t stream_) {
+    using namespace vb;
+    (void)partial;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(dy && x && gamma && mean && rstd && dx, "vb_layernorm_bwd: null pointer");
+    VB_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 2048, "vb_layernorm_bwd: cols=%d must be a multiple of 8, <= 2048", cols);
+    const int chunks = (cols / 8 + 31) / 32;
+    int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+    const int max_grid = num_sms() * 4;
+    if (grid > max_grid) grid = max_grid;
+    VB_LN_DISPATCH(chunks, (layernorm_bwd_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(
+                               static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd,
+                               static_cast<const bf16*>(dres), static_cast<bf16*>(dx), dgamma, dbeta, rows, cols)));
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+extern "C" int vb_layernorm_pair_sqdiff(const float* a, const float* b, float* u, int32_t n_samples,
+                                        int32_t rows_per_sample, int32_t cols, float eps, vb_stream_t stream_) {
+    using namespace vb;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(a && b && u, "vb_layernorm_pair_sqdiff: null pointer");
+    VB_CHECK_ARG(n_samples > 0 && rows_per_sample > 0 && cols % 4 == 0 && cols <= 1024 * 1, "vb_layernorm_pair_sqdiff: cols=%d must be a multiple of 4, <= 1024", cols);
+    const int chunks = (cols / 4 + 31) / 32;
+    dim3 grid(n_samples, (rows_per_sample + LN_WARPS * 4 - 1) / (LN_WARPS * 4));
+    VB_LN_DISPATCH(chunks, (layernorm_pair_sqdiff_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(a, b, u, n_samples,
+                                                                                                  rows_per_sample, cols, eps)));
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
