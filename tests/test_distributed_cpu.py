@@ -1,0 +1,123 @@
+"""CPU suite: the N>1 path on world_size-2 `gloo` — bucketed gradient averaging == single-process gradient on the
+concatenated batch; frozen parameters are excluded from the buckets; pair sharding covers every unit exactly once."""
+
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_model():
+    torch.manual_seed(0)
+    return nn.Sequential(nn.Linear(16, 32), nn.GELU(), nn.Linear(32, 32), nn.LayerNorm(32), nn.Linear(32, 4))
+
+
+def _worker(rank, world, port, bucket_mb, freeze_first, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from vit_plasticity_b200.distributed import DataParallel
+    from vit_plasticity_b200.finetune import train_step
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _make_model()
+        if rank == 1:  # replicas start different on purpose: the wrapper must broadcast rank 0's weights
+            with torch.no_grad():
+                for p in model.parameters():
+                    p.add_(1.0)
+        if freeze_first:
+            for p in model[0].parameters():
+                p.requires_grad = False
+        dp = DataParallel(model, bucket_mb=bucket_mb)
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(8, 16, generator=g), torch.randint(0, 4, (8,), generator=g)
+        lo, hi = rank * 4, rank * 4 + 4
+        opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
+        loss = torch.nn.functional.cross_entropy(dp(x[lo:hi]), y[lo:hi])
+        loss.backward()
+        dp.finish_grad_sync()
+        grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        gnorm = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        # a second step through the public train_step helper (hooks must re-arm after zero_grad)
+        train_step(dp, opt, [(x[lo:hi], y[lo:hi])], grad_clip=1.0, after_backward=dp.finish_grad_sync)
+        torch.save((rank, grads, float(gnorm), {k: v.clone() for k, v in model.state_dict().items()}, len(dp.buckets), dp.grad_bytes()), os.path.join(outdir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket_mb,freeze_first", [(64, False), (0.002, False), (0.002, True)])
+def test_two_rank_gloo_matches_single_process(bucket_mb, freeze_first, tmp_path):
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, bucket_mb, freeze_first, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    results = [torch.load(tmp_path / f"r{r}.pt", weights_only=False) for r in range(2)]
+    # single-process reference on the concatenated batch
+    model = _make_model()
+    if freeze_first:
+        for p in model[0].parameters():
+            p.requires_grad = False
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(8, 16, generator=g), torch.randint(0, 4, (8,), generator=g)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
+    for _ in range(2):
+        loss = torch.nn.functional.cross_entropy(model(x), y)
+        loss.backward()
+        if _ == 0:
+            ref_grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        ref_norm = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        if _ == 0:
+            first_norm = float(ref_norm)
+        opt.step()
+        opt.zero_grad()
+    for rank, grads, gnorm, sd, n_buckets, nbytes in results:
+        assert set(grads) == set(ref_grads)
+        for k in ref_grads:
+            assert torch.allclose(grads[k], ref_grads[k], atol=1e-6), (rank, k)
+        assert abs(gnorm - first_norm) < 1e-5
+        for k, v in model.state_dict().items():
+            assert torch.allclose(sd[k], v, atol=1e-6), (rank, k)
+        trainable = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        assert nbytes == 4 * trainable  # frozen parameters never enter a bucket
+        assert n_buckets >= (2 if bucket_mb < 1 else 1)
+
+
+def test_shard_range_partitions_units():
+    from vit_plasticity_b200.distributed import shard_range
+
+    for n, world in [(65536, 8), (64, 8), (10, 4), (3, 8), (0, 2)]:
+        seen = []
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            assert 0 <= lo <= hi <= n
+            seen += list(range(lo, hi))
+        assert seen == list(range(n))
+
+
+def test_env_contract_without_torchrun(monkeypatch):
+    from vit_plasticity_b200 import distributed as D
+
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    assert not D.is_distributed_job() and D.get_rank() == 0 and D.get_world_size() == 1 and D.is_master_process()
+    mgr = D.build_manager({"device": "cpu", "bogus": 1})
+    with mgr as m:
+        model = m.build_model(nn.Linear(2, 2))
+        assert isinstance(model, nn.Linear)  # single process: no wrapper, as in the reference
+    with pytest.raises(NotImplementedError):
+        D.build_manager({"device": "cpu", "tp": 2, "dp": 1})

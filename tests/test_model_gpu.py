@@ -1,0 +1,288 @@
+"""Model-level parity on the GPU: the CUDA path (through the nn.Module drop-in surface and the C-ABI) against
+(a) the committed fixtures = outputs of the REAL reference in fp32, and (b) the CPU oracle on the same seeded inputs.
+
+Stated tolerances (bf16 storage / fp32 accumulate vs the reference's fp32):
+  logits        relative L2 error <= 2e-2   (observed bf16-vs-fp32 max abs 0.02 on ~1-magnitude logits)
+  loss          abs <= 2e-2
+  gradients     per-tensor relative L2 error <= 4e-2, total grad-norm within 2e-2 relative
+  plasticity    independent pairs: ratios within 2e-2 relative (attention), 5e-3 (LayerNorm / fc1 / fc2)
+"""
+
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+DEV = "cuda"
+REPORT = {}
+
+
+def _dump_report():
+    out = Path(__file__).resolve().parents[1] / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        (out / "parity_report.json").write_text(json.dumps(REPORT, indent=1, sort_keys=True))
+    except OSError:
+        pass
+
+
+def load(name):
+    return torch.load(GOLDEN / f"{name}.pt", weights_only=False)
+
+
+def arch_of(gold):
+    a = dict(gold["arch"])
+    a["image_dim"] = tuple(a["image_dim"])
+    return O.Arch(**a)
+
+
+def rel_l2(got, ref):
+    got, ref = torch.as_tensor(got).double().cpu(), torch.as_tensor(ref).double().cpu()
+    return float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+def build(name, gold, arch, sd):
+    from vit_plasticity_b200 import build_model
+
+    if name == "vit_base":
+        cfg = dict(implementation="vit", model_name="base", pretrained=False, in21k=True, finetuning=True, n_classes=arch.n_classes)
+        model = build_model(cfg, device=DEV)
+        model.load_state_dict({"model." + k: v for k, v in sd.items()})
+    else:
+        cfg = dict(implementation="transformer", image_dim=arch.image_dim, patch_type="computer_vision", image_patch="hybrid",
+                   patch_size=arch.patch_size, emb_type="linear", emb_dim=arch.emb_dim, pos_emb=True, n_heads=arch.n_heads,
+                   attn_bias=True, activation="gelu", ffn_dim=arch.ffn_dim, ffn_bias=True, norm="layer", norm_bias=True,
+                   norm_eps=arch.norm_eps, pre_norm=True, n_layers=arch.n_layers, cls_token=True, output_type="classification",
+                   weight_tying=False, n_classes=arch.n_classes)
+        model = build_model(cfg, device=DEV)
+        model.load_state_dict(sd)
+    assert sorted(model.state_dict()) == gold["state_dict_keys"]
+    return model
+
+
+def check_summary(got, summ, tol, what):
+    got = got.detach().float().cpu()
+    if "full" in summ:
+        err = rel_l2(got, summ["full"])
+    else:
+        sample = got.flatten()[:: summ["stride"]][:256]
+        # sampled relative error, normalised by the full tensor's RMS so that near-zero samples do not dominate
+        rms = summ["norm"] / max(1.0, got.numel() ** 0.5)
+        err = float((sample.double() - summ["sample"].double()).norm() / (256**0.5 * rms + 1e-30))
+        nerr = abs(float(got.double().norm()) - summ["norm"]) / (summ["norm"] + 1e-30)
+        err = max(err, nerr)
+    REPORT.setdefault("grad_rel_l2", {})[what] = err
+    assert err <= tol, f"{what}: relative error {err:.3e} > {tol}"
+    return err
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "vit_base"])
+def test_logits_loss_grads_match_reference(name):
+    from vit_plasticity_b200.finetune import freeze_model
+
+    gold = load(name)
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    model = build(name, gold, arch, sd)
+    x = O.synthetic_images(gold["batch"], arch, gold["x_seed"]).to(DEV)
+    y = O.synthetic_labels(gold["batch"], arch, gold["y_seed"]).to(DEV)
+    model.train()
+    prefix = "model." if name == "vit_base" else ""
+    for fs, ref in gold["train"].items():
+        for p in model.parameters():
+            p.requires_grad_(True)
+            p.grad = None
+        freeze_model(model, ref["components"]) if prefix else _freeze_inner(model, ref["components"])
+        logits = model(x)
+        assert logits.dtype == torch.float32 and logits.shape == gold["logits"].shape
+        e_log = rel_l2(logits, gold["logits"])
+        loss = torch.nn.functional.cross_entropy(logits, y)
+        loss.backward()
+        grads = {k[len(prefix):]: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        assert sorted(grads) == ref["trainable"], f"{name}/{fs}: trainable set differs"
+        assert sum(g.numel() for g in grads.values()) == ref["n_trainable"]
+        gnorm = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())))
+        REPORT[f"{name}/{fs}"] = {"logits_rel_l2": e_log, "loss_abs": abs(float(loss) - ref["loss"]), "grad_norm_rel": abs(gnorm - ref["grad_norm"]) / ref["grad_norm"]}
+        assert e_log <= 2e-2, f"{name}/{fs}: logits rel L2 {e_log:.3e}"
+        assert abs(float(loss) - ref["loss"]) <= 2e-2
+        assert abs(gnorm - ref["grad_norm"]) <= 2e-2 * ref["grad_norm"], f"grad norm {gnorm} vs {ref['grad_norm']}"
+        worst = max(check_summary(g, ref["grads"][k], 4e-2, f"{name}/{fs}/{k}") for k, g in grads.items())
+        REPORT[f"{name}/{fs}"]["worst_grad_rel_l2"] = worst
+    _dump_report()
+
+
+def _freeze_inner(model, comps):
+    from vit_plasticity_b200.finetune import freeze_model
+
+    freeze_model(model, comps)
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_against_cpu_oracle_same_inputs(name):
+    """Same check against the oracle run here on the host (different seeds than the fixture)."""
+    gold = load(name)
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=7)
+    model = build(name, gold, arch, sd)
+    x = O.synthetic_images(5, arch, 21)
+    y = O.synthetic_labels(5, arch, 22)
+    o_loss, o_logits, o_grads = O.loss_and_grads(sd, x, y, arch)
+    model.train()
+    logits = model(x.to(DEV))
+    loss = torch.nn.functional.cross_entropy(logits, y.to(DEV))
+    loss.backward()
+    assert rel_l2(logits, o_logits) <= 2e-2
+    assert abs(float(loss) - float(o_loss)) <= 2e-2
+    for k, p in model.named_parameters():
+        assert rel_l2(p.grad, o_grads[k]) <= 4e-2, k
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "vit_base"])
+def test_train_step_matches_reference(name):
+    from vit_plasticity_b200.finetune import build_optimizer, train_step
+
+    gold = load(name)
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    model = build(name, gold, arch, sd)
+    prefix = "model." if name == "vit_base" else ""
+    ref = gold["train"]["full"]
+    x = O.synthetic_images(gold["batch"], arch, gold["x_seed"]).to(DEV)
+    y = O.synthetic_labels(gold["batch"], arch, gold["y_seed"]).to(DEV)
+    model.train()
+    opt = build_optimizer(model, "sgd", lr=1e-2, momentum=0.9)
+    loss, gnorm = train_step(model, opt, [(x, y)], grad_clip=1.0)
+    assert abs(float(loss) - ref["loss"]) <= 2e-2
+    assert abs(float(gnorm) - ref["grad_norm"]) <= 2e-2 * ref["grad_norm"]
+    new = {k[len(prefix):]: v for k, v in model.state_dict().items()}
+    worst = 0.0
+    for k, dn in ref["param_delta_norm"].items():
+        got = float((new[k].cpu().double() - sd[k].double()).norm())
+        worst = max(worst, abs(got - dn) / (dn + 1e-30))
+    REPORT[f"{name}/train_step_worst_delta_norm_rel"] = worst
+    assert worst <= 5e-2
+    assert all(p.grad is None for p in model.parameters())  # optimizer.zero_grad() ran
+    # two micro-batches with grad accumulation == one batch of the concatenation (mean-of-means, equal sizes)
+    model.load_state_dict({prefix + k: v for k, v in sd.items()})
+    opt = build_optimizer(model, "sgd", lr=1e-2, momentum=0.9)
+    h = gold["batch"] // 2
+    loss2, gnorm2 = train_step(model, opt, [(x[:h], y[:h]), (x[h : 2 * h], y[h : 2 * h])], grad_clip=1.0)
+    if 2 * h == gold["batch"]:
+        assert abs(float(gnorm2) - ref["grad_norm"]) <= 3e-2 * ref["grad_norm"]
+    _dump_report()
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "vit_base"])
+def test_plasticity_matches_reference(name):
+    from vit_plasticity_b200.plasticity import PlasticityEstimator, get_plasticity
+
+    gold = load(name)
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    model = build(name, gold, arch, sd).eval()
+    p = gold["plasticity"]
+    x1 = O.synthetic_images(p["n_pairs"], arch, p["x1_seed"]).to(DEV)
+    x2 = O.synthetic_images(p["n_pairs"], arch, p["x2_seed"]).to(DEV)
+    est = PlasticityEstimator(model)
+    dist = est.pair_distances(x1, x2)
+    assert list(dist) == p["keys"]
+    worst = {}
+    for k, ref in p["distances"].items():
+        comp = k.split("_", 1)[1] if "_" in k else k
+        err = float(np.max(np.abs(dist[k] - ref.numpy()) / ref.numpy()))
+        worst[comp] = max(worst.get(comp, 0.0), err)
+    ratios = get_plasticity(dist)
+    for comp, per_layer in ratios.items():
+        tol = 2e-2 if comp == "attn" else 5e-3
+        for i, r in enumerate(per_layer):
+            ref = p["ratios"][f"block{i}_{comp}"].numpy()
+            err = float(np.max(np.abs(r - ref) / ref))
+            worst["ratio_" + comp] = max(worst.get("ratio_" + comp, 0.0), err)
+            assert err <= tol, f"{name}: plasticity {comp}[{i}] rel err {err:.3e} > {tol}"
+    REPORT[f"{name}/plasticity_worst_rel"] = worst
+    # size-independent properties: identical inputs -> all distances exactly 0; symmetry in (x1, x2)
+    same = est.pair_distances(x1, x1)
+    assert all(float(np.abs(v).max()) == 0.0 for v in same.values())
+    swapped = est.pair_distances(x2, x1)
+    for k in dist:
+        assert np.allclose(swapped[k], dist[k], rtol=2e-3), k
+    # small perturbations: x' = x + eps * noise (fixture holds the fp32 reference ratios)
+    noise = O.synthetic_images(p["n_pairs"], arch, gold["plasticity_eps_noise_seed"]).to(DEV)
+    for eps, ref_r in gold["plasticity_eps"].items():
+        d = est.pair_distances(x1, x1 + eps * noise)
+        errs = {}
+        for k, r in ref_r.items():
+            comp = k.split("_", 1)[1]
+            errs[comp] = max(errs.get(comp, 0.0), float(np.max(np.abs(d[k] / d["embedding"] - r.numpy()) / r.numpy())))
+        REPORT[f"{name}/plasticity_eps_{eps}"] = errs
+        for comp in ("ffn_fc1", "ffn_fc2"):  # linear components run on the fp32 difference: eps-independent accuracy
+            assert errs[comp] <= 5e-3, f"{name}: eps={eps} {comp} rel err {errs[comp]:.3e}"
+    _dump_report()
+
+
+def test_decomposition_and_probes_api_tiny():
+    gold = load("tiny")
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    model = build("tiny", gold, arch, sd).eval()
+    x = O.synthetic_images(gold["batch"], arch, gold["x_seed"])
+    probes = model.get_probes(x.to(DEV))
+    assert list(probes) == list(gold["probes"])
+    for k, v in probes.items():
+        assert v.device.type == "cpu" and v.dtype == torch.float32
+        assert rel_l2(v[:, 0, :], gold["probes"][k]["cls"]) <= 3e-2, k
+        assert rel_l2(v.mean(1), gold["probes"][k]["mean"]) <= 3e-2, k
+    dec = model.get_decomposition(x.to(DEV))
+    ref = O.decomposition(sd, x, arch)
+    assert list(dec) == list(ref) and len(dec) == 1 + 5 * arch.n_layers
+    for k, v in dec.items():
+        assert v.device.type == "cpu" and v.shape == ref[k].shape
+        assert rel_l2(v, ref[k].detach()) <= 2e-2, k
+    # verbose=True returns the attention maps (n_layers, N, h, L, L), rows summing to one
+    logits, att = model(x.to(DEV), verbose=True)
+    assert att.shape == (arch.n_layers, gold["batch"], arch.n_heads, arch.seq_len, arch.seq_len)
+    assert torch.allclose(att.sum(-1), torch.ones_like(att.sum(-1)), atol=1e-3)
+    assert rel_l2(logits, gold["logits"]) <= 2e-2
+
+
+def test_block_forward_backward_vs_oracle():
+    from vit_plasticity_b200.models import TransformerConfig
+    from vit_plasticity_b200.models.layers import TransformerBlock
+
+    arch = O.Arch(emb_dim=256, n_heads=4, n_layers=1, ffn_dim=1024, image_dim=(3, 64, 64))
+    sd = O.init_state_dict(arch, seed=3)
+    cfg = TransformerConfig(emb_dim=256, n_heads=4, ffn_dim=1024, attn_bias=True, ffn_bias=True, norm="layer", norm_bias=True, norm_eps=1e-12)
+    blk = TransformerBlock(cfg).to(DEV)
+    blk.load_state_dict({k[len("blocks.0."):]: v for k, v in sd.items() if k.startswith("blocks.0.")})
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 17, 256, generator=g)
+    dy = torch.randn(3, 17, 256, generator=g)
+    xr = x.clone().requires_grad_(True)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.block(params, 0, xr, arch)
+    ref.backward(dy)
+    xg = x.to(DEV).requires_grad_(True)
+    out = blk(xg)
+    assert out.dtype == torch.float32  # fp32 in -> fp32 out at the module boundary
+    out.backward(dy.to(DEV))
+    assert rel_l2(out, ref.detach()) <= 1e-2
+    assert rel_l2(xg.grad, xr.grad) <= 3e-2
+    for k, p in blk.named_parameters():
+        assert rel_l2(p.grad, params["blocks.0." + k].grad) <= 3e-2, k
+
+
+def test_no_cpu_fallback():
+    from vit_plasticity_b200 import build_model
+
+    model = build_model({"implementation": "transformer", "image_dim": (3, 32, 32), "patch_type": "computer_vision", "emb_type": "linear",
+                         "emb_dim": 128, "n_heads": 2, "n_layers": 1, "attn_bias": True, "ffn_bias": True, "norm_bias": True,
+                         "cls_token": True, "output_type": "classification", "n_classes": 3}, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(1, 3, 32, 32))

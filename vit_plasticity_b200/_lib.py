@@ -96,6 +96,9 @@ SIGNATURES = {
 }
 
 _lib = None
+# bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream:
+# entries are (start_event, end_event, algorithmic_flops)
+GEMM_EVENTS = None
 
 
 def lib() -> ctypes.CDLL:
@@ -197,7 +200,14 @@ def gemm(
         args.sumsq = sumsq.data_ptr()
     args.rows_per_sample, args.cols_per_group, args.n_groups = rows_per_sample, cols_per_group, n_groups
     args.split_k = split_k
+    events = GEMM_EVENTS
+    if events is not None:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
     _check(lib().vb_gemm_bf16(ctypes.byref(args), _stream()), "vb_gemm_bf16")
+    if events is not None:
+        end.record()
+        events.append((start, end, 2.0 * m * n * k))
 
 
 # --------------------------------------------------------------------------------------------------

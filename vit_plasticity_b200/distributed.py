@@ -1,0 +1,217 @@
+"""Data-parallel finetuning: torchrun environment contract + bucketed, backward-overlapped gradient all-reduce.
+
+Reference: src/vitef/distributed.py. Its env helpers (48-89), ``ComputingManagerConfig`` (140-159) and the
+``ComputingManager`` context manager (162-250: ``init_process_group(backend="cpu:gloo,cuda:nccl")`` at 203, device =
+``cuda:{LOCAL_RANK}`` at 205, ``DDP(model)`` at 240) are mirrored for the DP branch. TP (232) and FSDP (237) are
+self-described work in progress there, have no caller and no plan, and are out of scope: ``tp > 1`` raises.
+
+``DataParallel`` is the DDP equivalent for this package. Built AFTER ``freeze_model`` so that frozen parameters are
+excluded, it packs the trainable parameters' gradients into flat fp32 buckets in reverse
+registration order (the order backward produces them), and, from post-accumulate-grad hooks, launches one asynchronous
+all-reduce per bucket (NCCL over NVLink 5 / NVSwitch on GPUs) as soon as the bucket is complete, so communication
+overlaps the rest of backward. ``p.grad`` is re-pointed at the bucket slot, so there is no copy-out, and
+``clip_grad_norm_`` / the optimizer see the averaged gradient (identical on every rank).
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+logger = logging.getLogger("vitef")
+
+
+def is_torchrun_job() -> bool:
+    return os.environ.get("LOCAL_RANK") is not None
+
+
+def is_distributed_job() -> bool:
+    return is_torchrun_job()
+
+
+def get_rank() -> int:
+    return int(os.environ["RANK"]) if is_torchrun_job() else 0
+
+
+def get_local_rank() -> int:
+    return int(os.environ["LOCAL_RANK"]) if is_torchrun_job() else 0
+
+
+def get_world_size() -> int:
+    return int(os.environ["WORLD_SIZE"]) if is_torchrun_job() else 1
+
+
+def is_master_process() -> bool:
+    return get_rank() == 0
+
+
+@dataclass
+class ComputingManagerConfig:
+    device: str = "cuda" if torch.cuda.is_available() else "cpu"
+    backend: str = "cpu:gloo,cuda:nccl"
+    dp: int = 0
+    tp: int = 1
+    bucket_mb: int = 64
+
+    def __post_init__(self) -> None:
+        if not self.dp:
+            self.dp = get_world_size() // self.tp
+
+
+class DataParallel(nn.Module):
+    """Gradient-averaging wrapper; ``forward`` delegates to the wrapped module."""
+
+    def __init__(self, module: nn.Module, process_group=None, bucket_mb: int = 64):
+        super().__init__()
+        self.module = module
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("DataParallel: the module has no trainable parameter")
+        cap = max(1, int(bucket_mb * 1024 * 1024 // 4))
+        self.buckets: list[torch.Tensor] = []
+        self._slot: dict[torch.Tensor, tuple[int, torch.Tensor]] = {}
+        self._expected: list[int] = []
+        cur: list[torch.Tensor] = []
+        cur_n = 0
+
+        def close():
+            nonlocal cur, cur_n
+            if not cur:
+                return
+            flat = torch.zeros(cur_n, device=cur[0].device, dtype=torch.float32)
+            off = 0
+            for p in cur:
+                self._slot[p] = (len(self.buckets), flat[off : off + p.numel()].view_as(p))
+                off += p.numel()
+            self.buckets.append(flat)
+            self._expected.append(len(cur))
+            cur, cur_n = [], 0
+
+        for p in reversed(params):  # gradients become ready roughly in reverse registration order
+            if p.dtype != torch.float32:
+                raise TypeError("DataParallel expects fp32 parameters")
+            if cur and cur_n + p.numel() > cap:
+                close()
+            cur.append(p)
+            cur_n += p.numel()
+        close()
+        self._ready = [0] * len(self.buckets)
+        self._handles: list = []
+        self._launched = [False] * len(self.buckets)
+        self.require_grad_sync = True
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        # replicas must start identical: broadcast rank 0's parameters and buffers
+        if self.world > 1:
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(self.module, name)
+
+    # ------------------------------------------------------------------------------------------
+    def _on_grad(self, p: torch.Tensor) -> None:
+        b, slot = self._slot[p]
+        if p.grad.data_ptr() != slot.data_ptr():
+            slot.copy_(p.grad)
+            p.grad = slot  # the optimizer / clip read (and zero_grad drops) the bucket view; no copy-out later
+        if not self.require_grad_sync:
+            return
+        self._ready[b] += 1
+        if self._ready[b] == self._expected[b] and not self._launched[b]:
+            self._launch(b)
+
+    def _launch(self, b: int) -> None:
+        self._launched[b] = True
+        if self.world > 1:
+            self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish_grad_sync(self) -> None:
+        """Call after the last backward of a step: flushes incomplete buckets (parameters that received no gradient
+        contribute zeros), waits for the collectives and turns sums into means."""
+        if not self.require_grad_sync:
+            return
+        for p, (b, slot) in self._slot.items():
+            if p.grad is None:
+                slot.zero_()
+                p.grad = slot
+        for b in range(len(self.buckets)):
+            if not self._launched[b]:
+                self._launch(b)
+        for h in self._handles:
+            h.wait()
+        if self.world > 1:
+            for flat in self.buckets:
+                flat.div_(self.world)
+        self._handles.clear()
+        self._ready = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+
+    def grad_bytes(self) -> int:
+        return sum(b.numel() * 4 for b in self.buckets)
+
+
+class ComputingManager:
+    """Context manager with the reference's contract (src/vitef/distributed.py:162-250), DP branch only."""
+
+    def __init__(self, config: ComputingManagerConfig):
+        self.config = config
+        self.backend = config.backend
+        self.device = torch.device(config.device)
+        self.tp, self.dp = config.tp, config.dp
+        if self.tp != 1:
+            raise NotImplementedError("tensor parallelism is a work-in-progress stub in the reference (distributed.py:224-233) and is out of scope")
+        nb = get_world_size()
+        assert self.device.type == "cpu" or self.dp * self.tp == nb, f"DP * TP must equal the number of GPUs {self.tp} * {self.dp} != {nb}"
+        os.environ.setdefault("OMP_NUM_THREADS", "1")  # OsEnvironment default, distributed.py:101
+
+    def __enter__(self):
+        if not is_distributed_job():
+            self.dp = self.tp = 1
+            return self
+        if self.device.type == "cuda":
+            self.device = torch.device(f"cuda:{get_local_rank()}")
+            torch.cuda.set_device(self.device)
+        dist.init_process_group(backend=self.backend, rank=get_rank(), world_size=get_world_size())
+        return self
+
+    def build_model(self, model: nn.Module) -> nn.Module:
+        model = model.to(device=self.device)
+        if self.dp > 1:
+            model = DataParallel(model, bucket_mb=self.config.bucket_mb)
+        return model
+
+    def __exit__(self, exc, value, tb):
+        if is_distributed_job() and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def build_manager(config: dict) -> ComputingManager:
+    known = {k: v for k, v in config.items() if k in ComputingManagerConfig.__dataclass_fields__}
+    return ComputingManager(ComputingManagerConfig(**known))
+
+
+def get_raw_model(model: nn.Module) -> nn.Module:
+    return get_raw_model(model.module) if isinstance(model, DataParallel) else model
+
+
+def shard_range(n_items: int, rank: int | None = None, world: int | None = None) -> tuple[int, int]:
+    """Contiguous shard [lo, hi) of ``n_items`` independent units (input pairs of the plasticity sweep) for this
+    rank; no collective is needed on the data path."""
+    rank = get_rank() if rank is None else rank
+    world = get_world_size() if world is None else world
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)

@@ -1,0 +1,379 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (``_lib``): the host side of the ViT Block hot path.
+
+Storage convention: parameters stay fp32 (the reference's ``state_dict`` schema); activations and activation
+gradients are bf16 2-D ``[tokens, features]`` tensors; every contraction accumulates in fp32 on tcgen05. A bf16
+shadow copy of each weight matrix is cached and refreshed when the parameter changes (optimizer step, load).
+
+Functions
+---------
+LayerNormFn   nn.LayerNorm                         (reference transformer/utils.py:293)
+LinearFn      nn.Linear, optional residual add     (architecture.py:205,236,295,297)
+AttentionFn   SelfAttention.forward (+ residual)   (architecture.py:189-239)
+MlpFn         FeedForward.forward (+ residual)     (architecture.py:281-299)
+BlockFn       TransformerBlock.forward, pre-norm   (architecture.py:369-374) — the training path; fuses the residual
+              gradient add into the LayerNorm backward so no stand-alone elementwise kernel runs per block
+EmbedFn       Embedding.forward for hybrid patches (architecture.py:644-678, transformer/utils.py:91,114)
+"""
+
+from __future__ import annotations
+
+import weakref
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+
+NUM_SMS = 148
+
+# --------------------------------------------------------------------------------------------------
+# bf16 shadow weights
+# --------------------------------------------------------------------------------------------------
+_shadow: "weakref.WeakKeyDictionary[torch.Tensor, tuple]" = weakref.WeakKeyDictionary()
+
+
+def shadow_bf16(p: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of an fp32 parameter viewed as [out_features, -1]; recast only when the parameter changed."""
+    key = (p.data_ptr(), p._version)
+    hit = _shadow.get(p)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    src = p.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    buf = hit[1] if hit is not None and hit[1].numel() == src.numel() and hit[1].device == src.device else None
+    w16 = L.cast_f32_to_bf16(src.view(src.shape[0], -1), buf)
+    _shadow[p] = (key, w16)
+    return w16
+
+
+def _f32c(p: torch.Tensor | None) -> torch.Tensor | None:
+    if p is None:
+        return None
+    d = p.detach()
+    return d if d.is_contiguous() else d.contiguous()
+
+
+def _wgrad_split_k(n_out: int, k_in: int, tokens: int) -> int:
+    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+    kb = (tokens + 63) // 64
+    sk = max(1, (2 * NUM_SMS) // tiles)
+    return max(1, min(sk, kb // 8 if kb >= 8 else 1))
+
+
+# --------------------------------------------------------------------------------------------------
+# functional building blocks (no autograd); x / dy are bf16 [tokens, features], contiguous
+# --------------------------------------------------------------------------------------------------
+def linear_fwd(x, w16, bias, *, residual=None, gelu=False):
+    m, k = x.shape
+    n = w16.shape[0]
+    out = torch.empty(m, n, device=x.device, dtype=torch.bfloat16)
+    if gelu:
+        z = torch.empty(m, n, device=x.device, dtype=torch.bfloat16)
+        L.gemm(x, w16, m=m, n=n, k=k, epilogue=L.EPI_BF16_GELU, bias=bias, out=out, out2=z)
+        return out, z
+    if residual is not None:
+        L.gemm(x, w16, m=m, n=n, k=k, epilogue=L.EPI_BF16_RESID, bias=bias, aux=residual, out=out)
+    else:
+        L.gemm(x, w16, m=m, n=n, k=k, epilogue=L.EPI_BF16, bias=bias, out=out)
+    return out
+
+
+def linear_dgrad(dy, w16, *, dgelu_z=None):
+    """dx = dy @ W (W stored [n_out, k_in], used as-is as an MN-major B operand); optional * gelu'(z)."""
+    m, n_out = dy.shape
+    k_in = w16.shape[1]
+    dx = torch.empty(m, k_in, device=dy.device, dtype=torch.bfloat16)
+    if dgelu_z is not None:
+        L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_DGELU, aux=dgelu_z, out=dx)
+    else:
+        L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16, out=dx)
+    return dx
+
+
+def linear_wgrad(dy, x, shape):
+    """dW = dy^T x in fp32 (split-K, TMA reduce-add into a zeroed buffer)."""
+    tokens, n_out = dy.shape
+    k_in = x.shape[1]
+    dw = torch.zeros(n_out, k_in, device=dy.device, dtype=torch.float32)
+    L.gemm(dy, x, m=n_out, n=k_in, k=tokens, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=_wgrad_split_k(n_out, k_in, tokens))
+    return dw.view(shape)
+
+
+def bias_grad(dy):
+    db = torch.zeros(dy.shape[1], device=dy.device, dtype=torch.float32)
+    L.colsum_bf16(dy, db)
+    return db
+
+
+def _as_bf16_2d(t: torch.Tensor) -> torch.Tensor:
+    t2 = t.reshape(-1, t.shape[-1])
+    if t2.dtype == torch.float32:
+        return L.cast_f32_to_bf16(t2.contiguous())
+    if t2.dtype != torch.bfloat16:
+        raise TypeError(f"expected float32 or bfloat16 activations, got {t2.dtype}")
+    return t2 if t2.is_contiguous() else t2.contiguous()
+
+
+def _like_input(out: torch.Tensor, in_dtype: torch.dtype) -> torch.Tensor:
+    """Modules return the dtype they were given: bf16 inside the model, fp32 for stand-alone fp32 callers."""
+    return L.cast_bf16_to_f32(out) if in_dtype == torch.float32 else out
+
+
+def _grad2d(g: torch.Tensor) -> torch.Tensor:
+    g2 = g.reshape(-1, g.shape[-1])
+    if g2.dtype != torch.bfloat16:
+        g2 = g2.to(torch.bfloat16)
+    return g2 if g2.is_contiguous() else g2.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# attention / mlp sub-graphs shared by the stand-alone Functions and BlockFn
+# --------------------------------------------------------------------------------------------------
+def _attn_fwd(h, wqkv16, bqkv, wo16, bo, residual, batch, seq, heads):
+    e = h.shape[1]
+    qkv = linear_fwd(h, wqkv16, bqkv)
+    o, lse = L.attention_fwd(qkv, batch, seq, heads, e // heads)
+    out = linear_fwd(o, wo16, bo, residual=residual)
+    return out, qkv, o, lse
+
+
+def _attn_bwd(dout, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need, batch, seq, heads):
+    """need = (dh, dWqkv, dbqkv, dWo, dbo)"""
+    e = o.shape[1]
+    dwo = linear_wgrad(dout, o, wo_shape) if need[3] else None
+    dbo = bias_grad(dout) if need[4] else None
+    if not (need[0] or need[1] or need[2]):
+        return None, None, None, dwo, dbo
+    do = linear_dgrad(dout, wo16)
+    dqkv = L.attention_bwd(qkv, o, do, lse, batch, seq, heads, e // heads)
+    dwqkv = linear_wgrad(dqkv, h, wqkv_shape) if need[1] else None
+    dbqkv = bias_grad(dqkv) if need[2] else None
+    dh = linear_dgrad(dqkv, wqkv16) if need[0] else None
+    return dh, dwqkv, dbqkv, dwo, dbo
+
+
+def _mlp_fwd(h, w116, b1, w216, b2, residual):
+    a, z = linear_fwd(h, w116, b1, gelu=True)
+    out = linear_fwd(a, w216, b2, residual=residual)
+    return out, z, a
+
+
+def _mlp_bwd(dout, h, z, a, w116, w216, w1_shape, w2_shape, need):
+    """need = (dh, dW1, db1, dW2, db2)"""
+    dw2 = linear_wgrad(dout, a, w2_shape) if need[3] else None
+    db2 = bias_grad(dout) if need[4] else None
+    if not (need[0] or need[1] or need[2]):
+        return None, None, None, dw2, db2
+    dz = linear_dgrad(dout, w216, dgelu_z=z)  # gelu'(z) fused into the fc2 dgrad epilogue
+    dw1 = linear_wgrad(dz, h, w1_shape) if need[1] else None
+    db1 = bias_grad(dz) if need[2] else None
+    dh = linear_dgrad(dz, w116) if need[0] else None
+    return dh, dw1, db1, dw2, db2
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd Functions
+# --------------------------------------------------------------------------------------------------
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        shape = x.shape
+        x2 = _as_bf16_2d(x)
+        w, b = _f32c(weight), _f32c(bias)
+        y, mean, rstd = L.layernorm_fwd(x2, w, b, eps)
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.in_dtype = x.dtype
+        ctx.shape = shape
+        return _like_input(y, x.dtype).view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dg = torch.zeros_like(w) if need_w else None
+        db = torch.zeros_like(w) if need_b else None
+        dx = L.layernorm_bwd(_grad2d(dy), x2, w, mean, rstd, dgamma=dg, dbeta=db)
+        dx = dx.view(ctx.shape)
+        if ctx.in_dtype != torch.bfloat16:
+            dx = dx.to(ctx.in_dtype)
+        return (dx if ctx.needs_input_grad[0] else None), dg, db, None
+
+
+class LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        shape = x.shape
+        x2 = _as_bf16_2d(x)
+        w16 = shadow_bf16(weight)
+        res2 = _as_bf16_2d(residual) if residual is not None else None
+        out = linear_fwd(x2, w16, _f32c(bias), residual=res2)
+        ctx.save_for_backward(x2, w16)
+        ctx.wshape = weight.shape
+        ctx.shape = shape
+        ctx.in_dtype = x.dtype
+        ctx.res_dtype = residual.dtype if residual is not None else None
+        return _like_input(out, x.dtype).view(*shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w16 = ctx.saved_tensors
+        dy2 = _grad2d(dy)
+        need = ctx.needs_input_grad
+        dx = linear_dgrad(dy2, w16).view(ctx.shape) if need[0] else None
+        if dx is not None and ctx.in_dtype != torch.bfloat16:
+            dx = dx.to(ctx.in_dtype)
+        dw = linear_wgrad(dy2, x2, ctx.wshape) if need[1] else None
+        db = bias_grad(dy2) if need[2] else None
+        dres = None
+        if need[3]:
+            dres = dy if ctx.res_dtype == dy.dtype else dy.to(ctx.res_dtype)
+        return dx, dw, db, dres
+
+
+class AttentionFn(Function):
+    """x -> output(softmax(q k^T / sqrt(d)) v) [+ residual]; x is [batch, seq, E]."""
+
+    @staticmethod
+    def forward(ctx, x, wqkv, bqkv, wo, bo, residual, heads):
+        batch, seq, e = x.shape
+        h = _as_bf16_2d(x)
+        wqkv16, wo16 = shadow_bf16(wqkv), shadow_bf16(wo)
+        res2 = _as_bf16_2d(residual) if residual is not None else None
+        out, qkv, o, lse = _attn_fwd(h, wqkv16, _f32c(bqkv), wo16, _f32c(bo), res2, batch, seq, heads)
+        ctx.save_for_backward(h, qkv, o, lse, wqkv16, wo16)
+        ctx.meta = (batch, seq, heads, wqkv.shape, wo.shape, x.dtype, residual.dtype if residual is not None else None)
+        return _like_input(out, x.dtype).view(batch, seq, e)
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, qkv, o, lse, wqkv16, wo16 = ctx.saved_tensors
+        batch, seq, heads, wqkv_shape, wo_shape, in_dtype, res_dtype = ctx.meta
+        need = ctx.needs_input_grad
+        d2 = _grad2d(dout)
+        dh, dwqkv, dbqkv, dwo, dbo = _attn_bwd(d2, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need[:5], batch, seq, heads)
+        if dh is not None:
+            dh = dh.view(batch, seq, -1)
+            if in_dtype != torch.bfloat16:
+                dh = dh.to(in_dtype)
+        dres = (dout if res_dtype == dout.dtype else dout.to(res_dtype)) if need[5] else None
+        return dh, dwqkv, dbqkv, dwo, dbo, dres, None
+
+
+class MlpFn(Function):
+    """x -> fc2(gelu(fc1(x))) [+ residual]"""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual):
+        shape = x.shape
+        h = _as_bf16_2d(x)
+        w116, w216 = shadow_bf16(w1), shadow_bf16(w2)
+        res2 = _as_bf16_2d(residual) if residual is not None else None
+        out, z, a = _mlp_fwd(h, w116, _f32c(b1), w216, _f32c(b2), res2)
+        ctx.save_for_backward(h, z, a, w116, w216)
+        ctx.meta = (shape, w1.shape, w2.shape, x.dtype, residual.dtype if residual is not None else None)
+        return _like_input(out, x.dtype).view(*shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, z, a, w116, w216 = ctx.saved_tensors
+        shape, w1_shape, w2_shape, in_dtype, res_dtype = ctx.meta
+        need = ctx.needs_input_grad
+        d2 = _grad2d(dout)
+        dh, dw1, db1, dw2, db2 = _mlp_bwd(d2, h, z, a, w116, w216, w1_shape, w2_shape, need[:5])
+        if dh is not None:
+            dh = dh.view(shape)
+            if in_dtype != torch.bfloat16:
+                dh = dh.to(in_dtype)
+        dres = (dout if res_dtype == dout.dtype else dout.to(res_dtype)) if need[5] else None
+        return dh, dw1, db1, dw2, db2, dres
+
+
+class BlockFn(Function):
+    """Pre-norm transformer block: out = x' + mlp(ln2(x')), x' = x + attn(ln1(x)).
+
+    Saved for backward (bf16): x, ln1(x), qkv, attention output, x', ln2(x'), fc1 pre-activation, gelu output,
+    plus fp32 mean/rstd/lse. Nothing else touches HBM: bias, GELU and both residual adds live in GEMM epilogues,
+    gelu' in the fc2-dgrad epilogue, and each residual-gradient add in the LayerNorm backward kernel.
+    """
+
+    @staticmethod
+    def forward(ctx, x, g1, be1, wqkv, bqkv, wo, bo, g2, be2, w1, b1, w2, b2, heads, eps):
+        batch, seq, e = x.shape
+        x2 = _as_bf16_2d(x)
+        g1c, be1c, g2c, be2c = _f32c(g1), _f32c(be1), _f32c(g2), _f32c(be2)
+        wqkv16, wo16, w116, w216 = shadow_bf16(wqkv), shadow_bf16(wo), shadow_bf16(w1), shadow_bf16(w2)
+        h1, mean1, rstd1 = L.layernorm_fwd(x2, g1c, be1c, eps)
+        xa, qkv, o, lse = _attn_fwd(h1, wqkv16, _f32c(bqkv), wo16, _f32c(bo), x2, batch, seq, heads)
+        h2, mean2, rstd2 = L.layernorm_fwd(xa, g2c, be2c, eps)
+        out, z, a = _mlp_fwd(h2, w116, _f32c(b1), w216, _f32c(b2), xa)
+        ctx.save_for_backward(x2, h1, mean1, rstd1, qkv, o, lse, xa, h2, mean2, rstd2, z, a, g1c, g2c, wqkv16, wo16, w116, w216)
+        ctx.meta = (batch, seq, heads, wqkv.shape, wo.shape, w1.shape, w2.shape, x.dtype)
+        return _like_input(out, x.dtype).view(batch, seq, e)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x2, h1, mean1, rstd1, qkv, o, lse, xa, h2, mean2, rstd2, z, a, g1c, g2c, wqkv16, wo16, w116, w216) = ctx.saved_tensors
+        batch, seq, heads, wqkv_shape, wo_shape, w1_shape, w2_shape, in_dtype = ctx.meta
+        n = ctx.needs_input_grad
+        d_out = _grad2d(dout)
+        # everything upstream of x' is needed if x, any attention parameter or either LN1 parameter wants a gradient
+        need_upstream = n[0] or any(n[1:7])
+        need_dh2 = need_upstream or n[7] or n[8]
+        # ---- MLP branch ----
+        dh2, dw1, db1, dw2, db2 = _mlp_bwd(d_out, h2, z, a, w116, w216, w1_shape, w2_shape, (need_dh2, n[9], n[10], n[11], n[12]))
+        dg2 = db_2 = None
+        d_xa = d_out
+        if dh2 is not None and (need_upstream or n[7] or n[8]):
+            dg2 = torch.zeros_like(g2c) if n[7] else None
+            db_2 = torch.zeros_like(g2c) if n[8] else None
+            d_xa = L.layernorm_bwd(dh2, xa, g2c, mean2, rstd2, dres=d_out, dgamma=dg2, dbeta=db_2)  # = dout + LN2'(dh2)
+        if not need_upstream:
+            return (None, None, None, None, None, None, None, dg2, db_2, dw1, db1, dw2, db2, None, None)
+        # ---- attention branch ----
+        need_dh1 = n[0] or n[1] or n[2]
+        dh1, dwqkv, dbqkv, dwo, dbo = _attn_bwd(d_xa, h1, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, (need_dh1, n[3], n[4], n[5], n[6]), batch, seq, heads)
+        dg1 = db_1 = None
+        dx = None
+        if dh1 is not None:
+            dg1 = torch.zeros_like(g1c) if n[1] else None
+            db_1 = torch.zeros_like(g1c) if n[2] else None
+            dx = L.layernorm_bwd(dh1, x2, g1c, mean1, rstd1, dres=d_xa, dgamma=dg1, dbeta=db_1)
+        if n[0]:
+            dx = (dx if dx is not None else d_xa).view(batch, seq, -1)
+            if in_dtype != torch.bfloat16:
+                dx = dx.to(in_dtype)
+        else:
+            dx = None
+        return (dx, dg1, db_1, dwqkv, dbqkv, dwo, dbo, dg2, db_2, dw1, db1, dw2, db2, None, None)
+
+
+class EmbedFn(Function):
+    """images f32 [N,C,H,W] -> tokens bf16 [N, 1 + n_patches, E] (im2col -> GEMM -> cls/pos assembly)."""
+
+    @staticmethod
+    def forward(ctx, img, conv_w, conv_b, cls, pos, patch):
+        n = img.shape[0]
+        e = conv_w.shape[0]
+        patches = L.im2col_patches(img.contiguous(), patch)
+        w16 = shadow_bf16(conv_w)  # [E, C*P*P]: K index = c*P*P + py*P + px, the Conv2d weight layout
+        po = linear_fwd(patches, w16, _f32c(conv_b))
+        np_ = patches.shape[0] // n
+        clsf, posf = _f32c(cls).reshape(-1), _f32c(pos).reshape(np_ + 1, e)
+        tokens, _ = L.assemble_tokens(po, None, clsf, posf, n, np_, e)
+        ctx.save_for_backward(patches)
+        ctx.meta = (n, np_, e, conv_w.shape, cls.shape, pos.shape)
+        return tokens.view(n, np_ + 1, e)
+
+    @staticmethod
+    def backward(ctx, dtok):
+        (patches,) = ctx.saved_tensors
+        n, np_, e, w_shape, cls_shape, pos_shape = ctx.meta
+        need = ctx.needs_input_grad
+        d2 = _grad2d(dtok)
+        dcls = torch.zeros(e, device=d2.device, dtype=torch.float32) if need[3] else None
+        dpos = torch.zeros(np_ + 1, e, device=d2.device, dtype=torch.float32) if need[4] else None
+        dpatch = L.assemble_tokens_bwd(d2, dcls, dpos, n, np_, e)
+        dw = linear_wgrad(dpatch, patches, w_shape) if need[1] else None
+        db = bias_grad(dpatch) if need[2] else None
+        return (None, dw, db, dcls.view(cls_shape) if dcls is not None else None, dpos.view(pos_shape) if dpos is not None else None, None)
