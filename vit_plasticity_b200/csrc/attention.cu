@@ -133,10 +133,12 @@ __device__ __forceinline__ void attn_row_block(const bf16* sQ, const bf16* sK, c
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-        o[nt][0] *= inv0;
-        o[nt][1] *= inv0;
-        o[nt][2] *= inv1;
-        o[nt][3] *= inv1;
+        // __fmul_rn: keeps the product a rounded value so that the paired variant's o_a - o_b cannot be contracted
+        // into an FMA (identical inputs must cancel exactly)
+        o[nt][0] = __fmul_rn(o[nt][0], inv0);
+        o[nt][1] = __fmul_rn(o[nt][1], inv0);
+        o[nt][2] = __fmul_rn(o[nt][2], inv1);
+        o[nt][3] = __fmul_rn(o[nt][3], inv1);
     }
 }
 

@@ -248,7 +248,8 @@ layernorm_pair_sqdiff_kernel(const float* __restrict__ a, const float* __restric
             if (c < nchunks) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float d = (va[i][j] - ma) * ra - (vb_[i][j] - mb) * rb;
+                    // __fmul_rn: no FMA contraction, so identical inputs cancel exactly
+                    const float d = __fmul_rn(va[i][j] - ma, ra) - __fmul_rn(vb_[i][j] - mb, rb);
                     acc[i][j] += d * d;
                 }
             }

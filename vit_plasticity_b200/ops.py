@@ -29,21 +29,29 @@ NUM_SMS = 148
 # --------------------------------------------------------------------------------------------------
 # bf16 shadow weights
 # --------------------------------------------------------------------------------------------------
-_shadow: "weakref.WeakKeyDictionary[torch.Tensor, tuple]" = weakref.WeakKeyDictionary()
+# id(param) -> (weakref to param, (data_ptr, version), bf16 tensor). Keyed by identity: tensors overload ``==``.
+_shadow: dict[int, tuple] = {}
 
 
 def shadow_bf16(p: torch.Tensor) -> torch.Tensor:
     """bf16 copy of an fp32 parameter viewed as [out_features, -1]; recast only when the parameter changed."""
     key = (p.data_ptr(), p._version)
-    hit = _shadow.get(p)
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    src = p.detach()
-    if not src.is_contiguous():
-        src = src.contiguous()
-    buf = hit[1] if hit is not None and hit[1].numel() == src.numel() and hit[1].device == src.device else None
-    w16 = L.cast_f32_to_bf16(src.view(src.shape[0], -1), buf)
-    _shadow[p] = (key, w16)
+    pid = id(p)
+    hit = _shadow.get(pid)
+    if hit is not None and hit[0]() is p:
+        if hit[1] == key:
+            return hit[2]
+    else:
+        hit = None
+    # the cached copy outlives this call: never create it as an inference tensor (get_probes / get_decomposition run
+    # under torch.inference_mode, a later training forward would fail to save it for backward)
+    with torch.inference_mode(False):
+        src = p.detach()
+        if not src.is_contiguous():
+            src = src.contiguous()
+        buf = hit[2] if hit is not None and hit[2].numel() == src.numel() and hit[2].device == src.device else None
+        w16 = L.cast_f32_to_bf16(src.view(src.shape[0], -1), buf)
+    _shadow[pid] = (weakref.ref(p, lambda _r, pid=pid: _shadow.pop(pid, None)), key, w16)
     return w16
 
 
