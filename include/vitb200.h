@@ -104,8 +104,10 @@ int vb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const fl
  * ------------------------------------------------------------------------------------------------ */
 int vb_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t seq, int32_t heads,
                      int32_t head_dim, vb_stream_t stream);
-/* dqkv: bf16 [batch*seq, 3*E]; dout: bf16 [batch*seq, E] */
-int vb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+/* dqkv: bf16 [batch*seq, 3*E]; dout: bf16 [batch*seq, E]; workspace: caller buffer of
+ * vb_attention_bwd_workspace_bytes(batch, seq, heads) bytes (holds delta = rowsum(dout * out), f32 [batch, heads, seq]). */
+int64_t vb_attention_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads);
+int vb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace,
                      int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
 /* Paired attention for the plasticity estimator: runs the core on qkv_a and qkv_b (same shapes) and writes
  * delta = attn(qkv_a) - attn(qkv_b), subtracted in fp32 before the bf16 down-cast. */

@@ -73,9 +73,10 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p],
     ),
     "vb_attention_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "vb_attention_bwd_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "vb_attention_bwd": (
         c_int32,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
     ),
     "vb_attention_pair_delta": (
         c_int32,
@@ -252,8 +253,9 @@ def attention_fwd(qkv, batch, seq, heads, head_dim, *, want_lse=True):
 
 def attention_bwd(qkv, out, dout, lse, batch, seq, heads, head_dim):
     dqkv = torch.empty_like(qkv)
+    ws = torch.empty(int(lib().vb_attention_bwd_workspace_bytes(batch, seq, heads)), device=qkv.device, dtype=torch.uint8)
     _check(
-        lib().vb_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), batch, seq, heads, head_dim, _stream()),
+        lib().vb_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), batch, seq, heads, head_dim, _stream()),
         "vb_attention_bwd",
     )
     return dqkv

@@ -9,6 +9,8 @@
 //   backward: warp owns 16-key blocks; computes S^T, dP^T in [key][query] layout so that P^T / dS^T feed the
 //             dV / dK MMAs directly; dS is transposed in registers (movmatrix) for dQ, accumulated in smem (fp32)
 //   pair    : forward on two inputs, writes attn(a) - attn(b) subtracted in fp32 (plasticity estimator)
+#include <stdlib.h>
+
 #include "host_utils.h"
 #include "ptx.cuh"
 
@@ -434,6 +436,24 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
     return VB_OK;
 }
 
+// tcgen05 implementations, used for seq <= 208 (ViT-B/L at 224x224)
+int launch_attention_bwd_tc(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int batch, int L,
+                            int H, cudaStream_t stream);  // attention_tc.cu: single kernel, P/dS through smem
+int launch_attention_fwd_tc2(const bf16* qkv, bf16* out, float* lse, int batch, int L, int H, cudaStream_t stream);
+int launch_attention_bwd_tc2(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
+                             int batch, int L, int H, cudaStream_t stream);  // attention_tc2.cu: 2 CTAs/SM, P/dS in TMEM
+
+// Development aid only (never set by the package): VITB200_ATTN=mma forces the legacy mma.sync kernels,
+// VITB200_ATTN=tc1 the single-kernel tcgen05 backward; default = the TMEM-operand kernels of attention_tc2.cu.
+static int attn_impl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VITB200_ATTN");
+        v = (e == nullptr) ? 2 : (e[0] == 'm' ? 0 : (e[0] == 't' && e[2] == '1' ? 1 : 2));
+    }
+    return v;
+}
+
 }  // namespace vb
 
 extern "C" int vb_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t seq, int32_t heads,
@@ -444,6 +464,8 @@ extern "C" int vb_attention_fwd(const void* qkv, void* out, float* lse, int32_t 
     VB_CHECK_ARG(head_dim == HD, "vb_attention_fwd: head_dim must be 64 (got %d)", head_dim);
     VB_CHECK_ARG(batch > 0 && heads > 0 && seq > 0 && seq <= 272, "vb_attention_fwd: seq=%d must be in [1, 272]", seq);
     const int64_t E = (int64_t)heads * HD;
+    if (seq <= 208 && attn_impl() == 2)
+        return launch_attention_fwd_tc2(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, batch, seq, heads, stream);
     if (seq <= 208)
         return launch_fwd<13, false>(static_cast<const bf16*>(qkv), nullptr, 3 * E, static_cast<bf16*>(out), E, lse, batch,
                                      seq, heads, stream);
@@ -463,13 +485,27 @@ extern "C" int vb_attention_pair_delta(const void* qkv_a, const void* qkv_b, int
                                 static_cast<bf16*>(delta), ld_delta, nullptr, batch, seq, heads, stream);
 }
 
+extern "C" int64_t vb_attention_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads) {
+    return (int64_t)batch * heads * seq * 4;
+}
+
 extern "C" int vb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                                int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream_) {
+                                void* workspace, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim,
+                                vb_stream_t stream_) {
     using namespace vb;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     VB_CHECK_ARG(qkv && out && dout && lse && dqkv, "vb_attention_bwd: null pointer");
     VB_CHECK_ARG(head_dim == HD, "vb_attention_bwd: head_dim must be 64 (got %d)", head_dim);
     VB_CHECK_ARG(batch > 0 && heads > 0 && seq > 0 && seq <= 272, "vb_attention_bwd: seq=%d must be in [1, 272]", seq);
+    if (seq <= 208 && attn_impl() == 2) {
+        VB_CHECK_ARG(workspace != nullptr, "vb_attention_bwd: workspace of vb_attention_bwd_workspace_bytes() bytes required");
+        return launch_attention_bwd_tc2(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
+                                        static_cast<const bf16*>(dout), lse, static_cast<float*>(workspace),
+                                        static_cast<bf16*>(dqkv), batch, seq, heads, stream);
+    }
+    if (seq <= 208 && attn_impl() == 1)
+        return launch_attention_bwd_tc(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
+                                       static_cast<const bf16*>(dout), lse, static_cast<bf16*>(dqkv), batch, seq, heads, stream);
     if (seq <= 208)
         return launch_bwd<13>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(dout),
                               lse, static_cast<bf16*>(dqkv), batch, seq, heads, stream);

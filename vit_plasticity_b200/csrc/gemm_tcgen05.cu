@@ -77,7 +77,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]     epilogue -> MMA
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-    const int warp = threadIdx.x >> 5;
+    // warp index through a shuffle: provably warp-uniform, so per-warp addresses / coordinates live in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -108,18 +109,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int total_work = p.num_m_blocks * p.num_n_blocks * p.split_k;
 
+    // The producer and MMA warps run their loops with ALL 32 lanes in uniform control flow and elect one lane only
+    // around the asynchronous instructions: addresses / descriptors stay in uniform registers. (With the whole loop
+    // under `if (lane == 0)` the compiler wrapped every UTCHMMA / UTMALDG in a divergence "waterfall" loop of ~20
+    // instructions, which made the single issuing thread the bottleneck.)
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const WorkItem it = decode_work(p, w);
-                for (int kb = it.kb0; kb < it.kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const WorkItem it = decode_work(p, w);
+            for (int kb = it.kb0; kb < it.kb1; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                uint8_t* sa = smem + stage * STAGE_BYTES;
+                uint8_t* sb = sa + A_STAGE_BYTES;
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
                     if (A_MN == 0) {
                         tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, it.m_blk * BM);
                     } else {
@@ -134,52 +139,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int i = 0; i < BN / 64; ++i)
                             tma_load_2d(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], it.n_blk * BN + i * 64, kb * BK);
                     }
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const WorkItem it = decode_work(p, w);
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+        // descriptor = constant high word (SBO 1024 B, version 1, SWIZZLE_128B) + low word (address, LBO)
+        constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        constexpr uint32_t lbo_a = A_MN == 0 ? 16u : (64u * BK * 2u), lbo_b = B_MN == 0 ? 16u : (64u * BK * 2u);
+        constexpr uint32_t kstep_a = (A_MN == 0 ? 32u : 2048u) >> 4, kstep_b = (B_MN == 0 ? 32u : 2048u) >> 4;
+        const uint32_t smem_lo = smem_u32(smem) >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const WorkItem it = decode_work(p, w);
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = it.kb0; kb < it.kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase, 3);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = it.kb0; kb < it.kb1; ++kb) {
-                    mbar_wait(&full_bar[stage], phase, 3);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t sb = sa + A_STAGE_BYTES;
+                // K-major : 8-row groups 1024 B apart (SBO), step 16 elements = 32 B inside the swizzle span
+                // MN-major: 64-element MN chunks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), step 16 k-rows = 2048 B
+                const uint32_t a_lo = (smem_lo + stage * (STAGE_BYTES >> 4)) | ((lbo_a >> 4) << 16);
+                const uint32_t b_lo = (smem_lo + stage * (STAGE_BYTES >> 4) + (A_STAGE_BYTES >> 4)) | ((lbo_b >> 4) << 16);
+                const uint32_t first = kb > it.kb0 ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // K-major : 8-row groups 1024 B apart (SBO), step 16 elements = 32 B inside the swizzle span
-                        // MN-major: 64-element MN chunks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO),
-                        //           step 16 k-rows = 2048 B
-                        const uint64_t adesc = A_MN == 0 ? make_smem_desc_sw128(sa + k * 32, 16, 1024)
-                                                         : make_smem_desc_sw128(sa + k * 2048, 64 * BK * 2, 1024);
-                        const uint64_t bdesc = B_MN == 0 ? make_smem_desc_sw128(sb + k * 32, 16, 1024)
-                                                         : make_smem_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024);
-                        umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16_ss(tmem_d, make_desc(a_lo + k * kstep_a, desc_hi), make_desc(b_lo + k * kstep_b, desc_hi), idesc,
+                                     k > 0 ? 1u : first);
                     umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
                 }
-                umma_commit(&tfull_bar[acc]);  // accumulator complete
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
+            if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete
+            __syncwarp();
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
         }
     } else if (warp >= EPI_FIRST_WARP) {
         // =========================== epilogue ===========================
@@ -249,7 +258,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             if (col0 + j < p.N) sumsq_local += f[j] * f[j];
                     } else if (epi == VB_EPI_F32 || epi == VB_EPI_F32_ADD) {
                         // 32 rows x 128 B, 16-byte chunk index XOR (row & 7) == TMA SWIZZLE_128B
-                        if (lane == 0) tma_store_wait_read<0>();
+                        if (elect_one()) tma_store_wait_read<0>();
                         __syncwarp();
                         const uint32_t rowaddr = smem_u32(stg) + lane * 128;
 #pragma unroll
@@ -261,7 +270,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (elect_one()) {
                             if (epi == VB_EPI_F32)
                                 tma_store_2d(&tmC, stg, col0, row0);
                             else
@@ -301,7 +310,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                         const bool two = (epi == VB_EPI_BF16_GELU);
                         uint8_t* b0 = stg + (two ? 0 : buf * 2048);
-                        if (lane == 0) {
+                        if (elect_one()) {
                             if (two)
                                 tma_store_wait_read<0>();
                             else
@@ -323,7 +332,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (elect_one()) {
                             tma_store_2d(&tmC, b0, col0, row0);
                             if (two) tma_store_2d(&tmC2, b0 + 2048, col0, row0);
                             tma_store_commit();
@@ -337,7 +346,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // all tcgen05.ld of this accumulator have completed (wait::ld above): hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (elect_one()) mbar_arrive(&tempty_bar[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
 
@@ -354,7 +363,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
         }
-        if (lane == 0) tma_store_wait_all<0>();
+        if (elect_one()) tma_store_wait_all<0>();
     }
 
     tc_fence_before();

@@ -78,6 +78,34 @@ int make_tensor_map_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_byt
     return VB_OK;
 }
 
+int make_tensor_map_3d(CUtensorMap* map, CUtensorMapDataType dtype, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,
+                       CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return VB_ERR_CUDA;
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0) {
+        set_error("TMA operand must be 16-byte aligned (ptr=%p, strides=%llu,%llu bytes)", ptr,
+                  (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes);
+        return VB_ERR_INVALID;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {box0, box1, box2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, dtype, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(3d) failed with CUresult %d (dims=%llu,%llu,%llu strides=%llu,%llu box=%u,%u,%u)", (int)r,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)stride1_bytes,
+                  (unsigned long long)stride2_bytes, box0, box1, box2);
+        return VB_ERR_CUDA;
+    }
+    return VB_OK;
+}
+
 }  // namespace vb
 
 extern "C" {

@@ -47,4 +47,9 @@ int make_tensor_map_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_byt
                        uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer,
                        CUtensorMapSwizzle swizzle);
 
+// 3-D tensor map (dims innermost first); strides[0] = bytes between rows of dim1, strides[1] = bytes between dim2 slabs.
+int make_tensor_map_3d(CUtensorMap* map, CUtensorMapDataType dtype, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,
+                       CUtensorMapSwizzle swizzle);
+
 }  // namespace vb

@@ -11,24 +11,43 @@ namespace vb {
 
 constexpr int LN_WARPS = 8;
 
+// Forward: persistent warps (grid = 6 blocks per SM), gamma / beta staged once per block in shared memory, the
+// next row's 128-bit loads are issued before the current row is reduced (two rows in flight per warp).
 template <int CHUNKS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int cols,
                      float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * LN_WARPS + warp;
-    if (row >= rows) return;
     const int nchunks = cols >> 3;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * cols);
-    float v[CHUNKS][8];
-    float sum = 0.f;
+    const int stride = gridDim.x * LN_WARPS;
+    __shared__ float sgamma[CHUNKS * 256], sbeta[CHUNKS * 256];
+    for (int i = threadIdx.x; i < CHUNKS * 256; i += LN_WARPS * 32) {
+        sgamma[i] = i < cols ? __ldg(gamma + i) : 0.f;
+        sbeta[i] = i < cols ? __ldg(beta + i) : 0.f;
+    }
+    __syncthreads();
+    int row = blockIdx.x * LN_WARPS + warp;
+    if (row >= rows) return;
+    uint4 cur[CHUNKS], nxt[CHUNKS];
+    auto load_row = [&](uint4(&dst)[CHUNKS], int r) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)r * cols);
 #pragma unroll
-    for (int i = 0; i < CHUNKS; ++i) {
-        const int c = lane + i * 32;
-        if (c < nchunks) {
-            const uint4 u = __ldg(xr + c);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            dst[i] = (c < nchunks) ? __ldg(xr + c) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    load_row(cur, row);
+    const float inv_cols = 1.f / (float)cols;
+    for (; row < rows; row += stride) {
+        const bool has_next = row + stride < rows;
+        if (has_next) load_row(nxt, row + stride);
+        float v[CHUNKS][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 f = unpack_bf16x2(w[j]);
@@ -36,141 +55,148 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma
                 v[i][2 * j + 1] = f.y;
                 sum += f.x + f.y;
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
         }
-    }
-    const float mean = warp_sum(sum) / (float)cols;
-    float sq = 0.f;
+        const float mean = warp_sum(sum) * inv_cols;
+        float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < CHUNKS; ++i) {
-        const int c = lane + i * 32;
-        if (c < nchunks) {
+        for (int i = 0; i < CHUNKS; ++i) {
+            if (lane + i * 32 < nchunks) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float d = v[i][j] - mean;
-                sq += d * d;
+                for (int j = 0; j < 8; ++j) {
+                    const float d = v[i][j] - mean;
+                    sq += d * d;
+                }
             }
         }
-    }
-    const float var = warp_sum(sq) / (float)cols;  // biased variance, as torch
-    const float rstd = rsqrtf(var + eps);
-    if (lane == 0) {
-        if (mean_out) mean_out[row] = mean;
-        if (rstd_out) rstd_out[row] = rstd;
-    }
-    uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * cols);
-#pragma unroll
-    for (int i = 0; i < CHUNKS; ++i) {
-        const int c = lane + i * 32;
-        if (c < nchunks) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c);
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
-            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
-            uint4 u;
-            u.x = pack_bf16x2(o[0], o[1]);
-            u.y = pack_bf16x2(o[2], o[3]);
-            u.z = pack_bf16x2(o[4], o[5]);
-            u.w = pack_bf16x2(o[6], o[7]);
-            yr[c] = u;
+        const float rstd = rsqrtf(warp_sum(sq) * inv_cols + eps);  // biased variance, as torch
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = mean;
+            if (rstd_out) rstd_out[row] = rstd;
         }
+        uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * cols);
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+                const float4 g0 = *reinterpret_cast<const float4*>(sgamma + c * 8);
+                const float4 g1 = *reinterpret_cast<const float4*>(sgamma + c * 8 + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(sbeta + c * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(sbeta + c * 8 + 4);
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+                uint4 u;
+                u.x = pack_bf16x2(o[0], o[1]);
+                u.y = pack_bf16x2(o[2], o[3]);
+                u.z = pack_bf16x2(o[4], o[5]);
+                u.w = pack_bf16x2(o[6], o[7]);
+                yr[c] = u;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) cur[i] = nxt[i];
     }
 }
 
+// Backward: persistent warps, gamma in shared memory, x / dy / dres of the NEXT row prefetched while the current row
+// is reduced; dgamma / dbeta partials live in registers across the row loop.
 template <int CHUNKS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
                      bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols) {
     __shared__ float red[LN_WARPS][32 * 8 + 1];
+    __shared__ float sgamma[CHUNKS * 256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = cols >> 3;
-    float dg[CHUNKS][8], db[CHUNKS][8], g[CHUNKS][8];
+    for (int i = threadIdx.x; i < CHUNKS * 256; i += LN_WARPS * 32) sgamma[i] = i < cols ? __ldg(gamma + i) : 0.f;
+    __syncthreads();
+    float dg[CHUNKS][8], db[CHUNKS][8];
 #pragma unroll
-    for (int i = 0; i < CHUNKS; ++i) {
-        const int c = lane + i * 32;
+    for (int i = 0; i < CHUNKS; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            dg[i][j] = 0.f;
-            db[i][j] = 0.f;
-            g[i][j] = (c < nchunks) ? __ldg(gamma + c * 8 + j) : 0.f;
-        }
-    }
+        for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
     const float inv_cols = 1.f / (float)cols;
-    for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
-        const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * cols);
-        const uint4* dyr = reinterpret_cast<const uint4*>(dy + (size_t)row * cols);
-        const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    const int stride = gridDim.x * LN_WARPS;
+    int row = blockIdx.x * LN_WARPS + warp;
+    uint4 cx[CHUNKS], cd[CHUNKS], cr[CHUNKS], nx[CHUNKS], nd[CHUNKS], nr[CHUNKS];
+    float cmu = 0.f, crs = 0.f, nmu = 0.f, nrs = 0.f;
+    auto load_row = [&](uint4(&ox)[CHUNKS], uint4(&od)[CHUNKS], uint4(&orr)[CHUNKS], float& mu, float& rs, int r) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)r * cols);
+        const uint4* dyr = reinterpret_cast<const uint4*>(dy + (size_t)r * cols);
+        const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + (size_t)r * cols) : nullptr;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            const bool ok = c < nchunks;
+            ox[i] = ok ? __ldg(xr + c) : make_uint4(0, 0, 0, 0);
+            od[i] = ok ? __ldg(dyr + c) : make_uint4(0, 0, 0, 0);
+            orr[i] = (ok && drr) ? __ldg(drr + c) : make_uint4(0, 0, 0, 0);
+        }
+        mu = __ldg(mean + r);
+        rs = __ldg(rstd + r);
+    };
+    if (row < rows) load_row(cx, cd, cr, cmu, crs, row);
+    for (; row < rows; row += stride) {
+        if (row + stride < rows) load_row(nx, nd, nr, nmu, nrs, row + stride);
+        const float mu = cmu, rs = crs;
         float xh[CHUNKS][8], gy[CHUNKS][8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < CHUNKS; ++i) {
             const int c = lane + i * 32;
-            if (c < nchunks) {
-                const uint4 ux = __ldg(xr + c), ud = __ldg(dyr + c);
-                const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w};
-                const uint32_t wd[4] = {ud.x, ud.y, ud.z, ud.w};
+            const uint32_t wx[4] = {cx[i].x, cx[i].y, cx[i].z, cx[i].w};
+            const uint32_t wd[4] = {cd[i].x, cd[i].y, cd[i].z, cd[i].w};
+            const float4 g0 = *reinterpret_cast<const float4*>(sgamma + c * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(sgamma + c * 8 + 4);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const bool ok = c < nchunks;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 fx = unpack_bf16x2(wx[j]);
-                    const float2 fd = unpack_bf16x2(wd[j]);
-                    const float h0 = (fx.x - mu) * rs, h1 = (fx.y - mu) * rs;
-                    xh[i][2 * j] = h0;
-                    xh[i][2 * j + 1] = h1;
-                    dg[i][2 * j] += fd.x * h0;
-                    dg[i][2 * j + 1] += fd.y * h1;
-                    db[i][2 * j] += fd.x;
-                    db[i][2 * j + 1] += fd.y;
-                    const float g0 = fd.x * g[i][2 * j], g1 = fd.y * g[i][2 * j + 1];
-                    gy[i][2 * j] = g0;
-                    gy[i][2 * j + 1] = g1;
-                    s1 += g0 + g1;
-                    s2 += g0 * h0 + g1 * h1;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    xh[i][j] = 0.f;
-                    gy[i][j] = 0.f;
-                }
+            for (int j = 0; j < 4; ++j) {
+                const float2 fx = unpack_bf16x2(wx[j]);
+                const float2 fd = unpack_bf16x2(wd[j]);
+                const float h0 = ok ? (fx.x - mu) * rs : 0.f, h1 = ok ? (fx.y - mu) * rs : 0.f;
+                xh[i][2 * j] = h0;
+                xh[i][2 * j + 1] = h1;
+                dg[i][2 * j] += fd.x * h0;
+                dg[i][2 * j + 1] += fd.y * h1;
+                db[i][2 * j] += fd.x;
+                db[i][2 * j + 1] += fd.y;
+                const float y0 = fd.x * g[2 * j], y1 = fd.y * g[2 * j + 1];
+                gy[i][2 * j] = y0;
+                gy[i][2 * j + 1] = y1;
+                s1 += y0 + y1;
+                s2 += y0 * h0 + y1 * h1;
             }
         }
         s1 = warp_sum(s1) * inv_cols;
         s2 = warp_sum(s2) * inv_cols;
         uint4* dxr = reinterpret_cast<uint4*>(dx + (size_t)row * cols);
-        const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + (size_t)row * cols) : nullptr;
 #pragma unroll
         for (int i = 0; i < CHUNKS; ++i) {
             const int c = lane + i * 32;
             if (c < nchunks) {
-                float o[8];
+                const uint32_t wr[4] = {cr[i].x, cr[i].y, cr[i].z, cr[i].w};
+                uint32_t o[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rs * (gy[i][j] - s1 - xh[i][j] * s2);
-                if (drr) {
-                    const uint4 ur = __ldg(drr + c);
-                    const uint32_t wr[4] = {ur.x, ur.y, ur.z, ur.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 fr = unpack_bf16x2(wr[j]);
-                        o[2 * j] += fr.x;
-                        o[2 * j + 1] += fr.y;
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const float2 fr = unpack_bf16x2(wr[j]);  // zeros when there is no residual gradient
+                    o[j] = pack_bf16x2(rs * (gy[i][2 * j] - s1 - xh[i][2 * j] * s2) + fr.x,
+                                       rs * (gy[i][2 * j + 1] - s1 - xh[i][2 * j + 1] * s2) + fr.y);
                 }
-                uint4 u;
-                u.x = pack_bf16x2(o[0], o[1]);
-                u.y = pack_bf16x2(o[2], o[3]);
-                u.z = pack_bf16x2(o[4], o[5]);
-                u.w = pack_bf16x2(o[6], o[7]);
-                dxr[c] = u;
+                dxr[c] = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            cx[i] = nx[i];
+            cd[i] = nd[i];
+            cr[i] = nr[i];
+        }
+        cmu = nmu;
+        crs = nrs;
     }
     if (dgamma == nullptr && dbeta == nullptr) return;  // frozen norm: parameter gradients not needed
     // block reduction of the per-warp partials, one chunk-slot at a time, then one atomic per column
@@ -286,7 +312,8 @@ extern "C" int vb_layernorm_fwd(const void* x, const float* gamma, const float* 
     VB_CHECK_ARG(x && gamma && beta && y, "vb_layernorm_fwd: null pointer");
     VB_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 2048, "vb_layernorm_fwd: cols=%d must be a multiple of 8, <= 2048", cols);
     const int chunks = (cols / 8 + 31) / 32;
-    const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+    int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
     VB_LN_DISPATCH(chunks, (layernorm_fwd_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(
                                static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y), mean, rstd, rows, cols, eps)));
     VB_CHECK_LAUNCH();
@@ -308,7 +335,7 @@ extern "C" int vb_layernorm_bwd(const void* dy, const void* x, const float* gamm
     VB_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 2048, "vb_layernorm_bwd: cols=%d must be a multiple of 8, <= 2048", cols);
     const int chunks = (cols / 8 + 31) / 32;
     int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-    const int max_grid = num_sms() * 4;
+    const int max_grid = num_sms() * 2;
     if (grid > max_grid) grid = max_grid;
     VB_LN_DISPATCH(chunks, (layernorm_bwd_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(
                                static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd,

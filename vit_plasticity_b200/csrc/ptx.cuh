@@ -181,6 +181,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -197,6 +203,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
     d |= static_cast<uint64_t>(1) << 46;
     d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// 64-bit descriptor from its two 32-bit halves (one MOV pair, keeps the halves in uniform registers)
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
     return d;
 }
 // instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulate.
@@ -219,13 +231,41 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
-// exact (erf) GELU, matching torch.nn.functional.gelu(approximate="none")
-__device__ __forceinline__ float gelu_erf(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Standard normal CDF Phi(z) = 0.5 (1 + erf(z / sqrt 2)) and e = exp(-z^2 / 2) with one MUFU.RCP + one MUFU.EX2:
+// Abramowitz-Stegun 7.1.26 for erfc (|abs error| <= 1.5e-7, three orders below bf16 output rounding), so this is the
+// EXACT-erf GELU of torch.nn.functional.gelu(approximate="none") to bf16 precision, not the tanh approximation.
+// (libdevice erff costs ~40 instructions per element and made the GELU / dGELU epilogues slower than the MMA.)
+__device__ __forceinline__ void normal_cdf_exp(float z, float& cdf, float& e) {
+    const float x = fabsf(z) * 0.70710678118654752f;
+    const float t = fast_rcp(fmaf(0.3275911f, x, 1.0f));
+    e = fast_ex2(-0.72134752044448170f * z * z);  // exp(-z^2/2) = 2^(-z^2 log2(e) / 2)
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float half_erfc = 0.5f * poly * t * e;  // 0.5 erfc(|z| / sqrt 2)
+    cdf = z >= 0.f ? 1.0f - half_erfc : half_erfc;
+}
+__device__ __forceinline__ float gelu_erf(float z) {
+    float cdf, e;
+    normal_cdf_exp(z, cdf, e);
+    return z * cdf;
+}
 // d/dz gelu(z) = Phi(z) + z * phi(z)
 __device__ __forceinline__ float dgelu_erf(float z) {
-    float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
-    float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
-    return cdf + z * pdf;
+    float cdf, e;
+    normal_cdf_exp(z, cdf, e);
+    return fmaf(z * 0.3989422804014327f, e, cdf);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
