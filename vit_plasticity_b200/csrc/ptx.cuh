@@ -245,26 +245,27 @@ __device__ __forceinline__ float fast_rcp(float x) {
 // Abramowitz-Stegun 7.1.26 for erfc (|abs error| <= 1.5e-7, three orders below bf16 output rounding), so this is the
 // EXACT-erf GELU of torch.nn.functional.gelu(approximate="none") to bf16 precision, not the tanh approximation.
 // (libdevice erff costs ~40 instructions per element and made the GELU / dGELU epilogues slower than the MMA.)
-__device__ __forceinline__ void normal_cdf_exp(float z, float& cdf, float& e) {
-    const float x = fabsf(z) * 0.70710678118654752f;
-    const float t = fast_rcp(fmaf(0.3275911f, x, 1.0f));
-    e = fast_ex2(-0.72134752044448170f * z * z);  // exp(-z^2/2) = 2^(-z^2 log2(e) / 2)
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float half_erfc = 0.5f * poly * t * e;  // 0.5 erfc(|z| / sqrt 2)
-    cdf = z >= 0.f ? 1.0f - half_erfc : half_erfc;
+// h = 0.5 erfc(|z| / sqrt 2) = 1 - Phi(|z|) and e = exp(-z^2 / 2)
+__device__ __forceinline__ void half_erfc_exp(float z, float& h, float& e) {
+    const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, fabsf(z), 1.0f));
+    e = fast_ex2(-0.72134752044448170f * (z * z));  // exp(-z^2/2) = 2^(-z^2 log2(e) / 2)
+    float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);  // the 0.5 of "half" is folded into the coefficients
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, 0.5f * -0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
+    h = poly * t * e;
 }
+// gelu(z) = z Phi(z) = relu(z) - |z| h   (z >= 0: z - z h ; z < 0: z h)
 __device__ __forceinline__ float gelu_erf(float z) {
-    float cdf, e;
-    normal_cdf_exp(z, cdf, e);
-    return z * cdf;
+    float h, e;
+    half_erfc_exp(z, h, e);
+    return fmaf(-fabsf(z), h, fmaxf(z, 0.f));
 }
-// d/dz gelu(z) = Phi(z) + z * phi(z)
+// d/dz gelu(z) = Phi(z) + z phi(z),  Phi(z) = z >= 0 ? 1 - h : h
 __device__ __forceinline__ float dgelu_erf(float z) {
-    float cdf, e;
-    normal_cdf_exp(z, cdf, e);
+    float h, e;
+    half_erfc_exp(z, h, e);
+    const float cdf = z >= 0.f ? 1.0f - h : h;
     return fmaf(z * 0.3989422804014327f, e, cdf);
 }
 
