@@ -440,16 +440,20 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
 int launch_attention_bwd_tc(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int batch, int L,
                             int H, cudaStream_t stream);  // attention_tc.cu: single kernel, P/dS through smem
 int launch_attention_fwd_tc2(const bf16* qkv, bf16* out, float* lse, int batch, int L, int H, cudaStream_t stream);
+int launch_attention_fwd_tc3(const bf16* qkv, bf16* out, float* lse, int batch, int L, int H, cudaStream_t stream);
+int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
+                             int batch, int L, int H, cudaStream_t stream);
 int launch_attention_bwd_tc2(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                              int batch, int L, int H, cudaStream_t stream);  // attention_tc2.cu: 2 CTAs/SM, P/dS in TMEM
 
 // Development aid only (never set by the package): VITB200_ATTN=mma forces the legacy mma.sync kernels,
-// VITB200_ATTN=tc1 the single-kernel tcgen05 backward; default = the TMEM-operand kernels of attention_tc2.cu.
+// VITB200_ATTN=tc1 the single-kernel tcgen05 backward, VITB200_ATTN=tc2 the one-CTA-per-tile TMEM-operand kernels of
+// attention_tc2.cu; default = the persistent pipelined kernels of attention_tc3.cu.
 static int attn_impl() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("VITB200_ATTN");
-        v = (e == nullptr) ? 2 : (e[0] == 'm' ? 0 : (e[0] == 't' && e[2] == '1' ? 1 : 2));
+        v = (e == nullptr) ? 3 : (e[0] == 'm' ? 0 : (e[0] == 't' && e[2] == '1' ? 1 : (e[0] == 't' && e[2] == '2' ? 2 : 3)));
     }
     return v;
 }
@@ -464,6 +468,8 @@ extern "C" int vb_attention_fwd(const void* qkv, void* out, float* lse, int32_t 
     VB_CHECK_ARG(head_dim == HD, "vb_attention_fwd: head_dim must be 64 (got %d)", head_dim);
     VB_CHECK_ARG(batch > 0 && heads > 0 && seq > 0 && seq <= 272, "vb_attention_fwd: seq=%d must be in [1, 272]", seq);
     const int64_t E = (int64_t)heads * HD;
+    if (seq <= 208 && attn_impl() == 3)
+        return launch_attention_fwd_tc3(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, batch, seq, heads, stream);
     if (seq <= 208 && attn_impl() == 2)
         return launch_attention_fwd_tc2(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, batch, seq, heads, stream);
     if (seq <= 208)
@@ -497,6 +503,12 @@ extern "C" int vb_attention_bwd(const void* qkv, const void* out, const void* do
     VB_CHECK_ARG(qkv && out && dout && lse && dqkv, "vb_attention_bwd: null pointer");
     VB_CHECK_ARG(head_dim == HD, "vb_attention_bwd: head_dim must be 64 (got %d)", head_dim);
     VB_CHECK_ARG(batch > 0 && heads > 0 && seq > 0 && seq <= 272, "vb_attention_bwd: seq=%d must be in [1, 272]", seq);
+    if (seq <= 208 && attn_impl() == 3) {
+        VB_CHECK_ARG(workspace != nullptr, "vb_attention_bwd: workspace of vb_attention_bwd_workspace_bytes() bytes required");
+        return launch_attention_bwd_tc3(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
+                                        static_cast<const bf16*>(dout), lse, static_cast<float*>(workspace),
+                                        static_cast<bf16*>(dqkv), batch, seq, heads, stream);
+    }
     if (seq <= 208 && attn_impl() == 2) {
         VB_CHECK_ARG(workspace != nullptr, "vb_attention_bwd: workspace of vb_attention_bwd_workspace_bytes() bytes required");
         return launch_attention_bwd_tc2(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
