@@ -1,20 +1,28 @@
 // Persistent, software-pipelined attention forward / backward on tcgen05 for L <= 208 tokens, head_dim = 64
 // (ViT-B/L at 224x224: L = 197). One CTA per SM walks over (image, head) items:
 //
-//   warp 8      TMA producer: the item's Q/K/V(/dO) rows as 208-row SWIZZLE_128B operand tiles (two 104-row boxes each;
-//               rows >= L are zero-filled by the TMA unit), double-buffered, so item i+1 loads while item i computes
-//   warp 9      MMA issuer (one elected lane): runs one unit ahead of the math warps, so the tensor pipe works on the
-//               next scores while the math warps exponentiate the current ones
-//   warps 0..7  math: TMEM -> registers -> TMEM. Probabilities never touch shared memory: they are packed to bf16 in
-//               place of the fp32 scores and consumed as the A operand (from TMEM) of the next MMA.
+//   warp 16      TMA producer: the item's Q/K/V(/dO) rows as 208-row SWIZZLE_128B operand tiles (two 104-row boxes
+//                each; rows >= L are zero-filled by the TMA unit), double-buffered: item i+1 loads while item i computes
+//   warp 17      MMA issuer (one elected lane): runs ahead of the math warps, so the tensor pipe works on the next
+//                scores while the math warps exponentiate the current ones
+//   warps 0..15  math: TMEM -> registers -> TMEM (4 warps per scheduler: the exp2 / FMA chains of one warp hide behind
+//                the others). Probabilities never touch shared memory: they are packed to bf16 over the fp32 scores
+//                and consumed as the A operand (from TMEM) of the next MMA.
 //
-// forward, per item two units (query tiles of 128 rows): S = Q_t K^T (N = 208) -> exact two-pass softmax -> O = P V.
+// forward, per item two units (query tiles of 128 rows): S = Q_t K^T (N = 208) -> exact softmax, one TMEM read, the row
+//   split over 4 warps (64+48+48+48 columns held in registers) -> O = P V.
 //   TMEM: S/P buffers [0,208) and [208,416) (unit parity), O accumulator [416,480).
 // backward, per item four units: dQ_t (t = 0,1; queries on the TMEM lanes) and dK_j/dV_j (j = 0,1; keys on the lanes,
 //   "transposed domain", so lse / delta are per-COLUMN scalars there). Each unit walks 4 column chunks (64,64,64,16):
 //   MMA1: S_c, dP_c -> math: P = exp2(S c - lse), dS = P (dP - delta) / 8 -> MMA2: accumulate.
-//   TMEM: chunk buffers [0,128) / [128,256) (S at +0, dP at +64), accumulators [256,384) / [384,512) (unit parity).
-//   No masking is needed: padded K/V/Q/dO rows are zero and padded lse entries are +inf (p = 0).
+//   TMEM: three chunk buffers [0,128) [128,256) [256,384) (S at +0, dP at +64), accumulator [384,512). Two issuer warps:
+//   warp 17 issues every MMA1 (three chunks ahead of the math), warp 18 every MMA2; a buffer returns to MMA1 when the
+//   MMA2 that read it has completed. The two math groups (8 warps each) take alternate chunks; group 1 also drains the
+//   accumulators. No masking is needed: padded K/V/Q/dO rows are zero and padded lse entries are +inf (p = 0).
+//   Measured (tools/microbench/mma_rate.cu): a 128xNx16 MMA costs ~44 + N/2 cycles with A in smem, ~12 + N/2 with A in
+//   TMEM, so these N = 64 tiles run the tensor pipe at < 50 % of its rate: head_dim 64 bounds this kernel, not HBM.
+#include <stdlib.h>
+
 #include "host_utils.h"
 #include "ptx.cuh"
 
@@ -26,9 +34,9 @@ constexpr int ROWS = 208;                    // operand rows staged per item (13
 constexpr int BOX_ROWS = 104;                // 104 x 128 B = 13 KB per TMA box, a multiple of the 1024-B swizzle atom
 constexpr int OPER_BYTES = ROWS * 128;       // 26624
 constexpr int TILE_BYTES = 128 * 128;        // second 128-row tile of an operand starts here
-constexpr int MATH_WARPS = 8;
-constexpr int WARP_TMA = 8, WARP_MMA = 9;
-constexpr int THREADS = 10 * 32;
+constexpr int MATH_WARPS = 16;
+constexpr int WARP_TMA = 16, WARP_MMA = 17;
+constexpr int THREADS = 18 * 32;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B | version 1 | SWIZZLE_128B
@@ -45,6 +53,16 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+        "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
 // The registers of an asynchronous tcgen05.ld are defined only after tcgen05.wait::ld: pin every later use behind it.
@@ -82,43 +100,82 @@ __device__ __forceinline__ void store_32cols_bf16(bf16* dst, const uint32_t (&a)
 // forward
 // =====================================================================================================
 constexpr int F_STAGE = 3 * OPER_BYTES;  // Q, K, V
-constexpr int F_EXCH_BYTES = 2 * 2 * 128 * 4 * 2;  // sMax / sSum: [unit parity][column half][row]
-constexpr int F_SMEM = 2 * F_STAGE + F_EXCH_BYTES + 256 + 1024;
+constexpr int F_EXCH_FLOATS = 2 * 4 * 128;  // sMax / sSum: [unit parity][column part][row]
+constexpr int F_SMEM = 2 * F_STAGE + 2 * F_EXCH_FLOATS * 4 + 256 + 1024;
 constexpr uint32_t F_COL_O = 416;
 
-// 16 scores -> running max (nvalid = number of unmasked columns among these 16)
-__device__ __forceinline__ float max16(const uint32_t (&v)[16], float m, int nvalid) {
-    if (nvalid >= 16) {
+// One row's share of the softmax: NC (64 or 48) scores at TMEM columns [cbeg, cbeg + NC) of the S buffer, held in
+// registers across the row-max exchange, exponentiated and packed to bf16 pairs at columns [cbeg / 2, +NC / 2).
+template <int NC>
+__device__ __forceinline__ void softmax_part(uint32_t s_buf, int cbeg, int nvalid, float c, float* sMaxU, float* sSumU, int part,
+                                             int row, int quarter, float& m_out, float& sum_out) {
+    uint32_t v0[32], v1[NC - 32];
+    tmem_ld_32x32b_x32(s_buf + cbeg, v0);
+    if constexpr (NC == 64)
+        tmem_ld_32x32b_x32(s_buf + cbeg + 32, v1);
+    else
+        tmem_ld_32x32b_x16(s_buf + cbeg + 32, v1);
+    tmem_ld_wait();
+    reg_fence(v0);
+    reg_fence(v1);
+    float m = -INFINITY;
+    if (nvalid >= NC) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v0[i]));
+#pragma unroll
+        for (int i = 0; i < NC - 32; ++i) m = fmaxf(m, __uint_as_float(v1[i]));
     } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (i < nvalid) m = fmaxf(m, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i)
+            if (i < nvalid) m = fmaxf(m, __uint_as_float(v0[i]));
+#pragma unroll
+        for (int i = 0; i < NC - 32; ++i)
+            if (32 + i < nvalid) m = fmaxf(m, __uint_as_float(v1[i]));
     }
-    return m;
-}
-// 16 scores -> 16 probabilities packed as 8 bf16 pairs; returns their fp32 sum
-__device__ __forceinline__ float exp16(const uint32_t (&v)[16], uint32_t (&pk)[8], float c, float mc, int nvalid) {
-    float p[16];
-    if (nvalid >= 16) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) p[i] = fast_ex2(fmaf(__uint_as_float(v[i]), c, -mc));
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) p[i] = (i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
+    sMaxU[part * 128 + row] = m;
+    named_bar_sync(1 + quarter, 128);  // the four warps sharing this lane quarter: all their S columns are in registers now
+    m = fmaxf(fmaxf(sMaxU[row], sMaxU[128 + row]), fmaxf(sMaxU[256 + row], sMaxU[384 + row]));  // column 0 is valid: finite
+    const float mc = m * c;
+    uint32_t pk0[16], pk1[(NC - 32) / 2];
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (nvalid >= NC) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        s0 += p[4 * i];
-        s1 += p[4 * i + 1];
-        s2 += p[4 * i + 2];
-        s3 += p[4 * i + 3];
+        for (int i = 0; i < 16; ++i) {
+            const float a = fast_ex2(fmaf(__uint_as_float(v0[2 * i]), c, -mc)), b = fast_ex2(fmaf(__uint_as_float(v0[2 * i + 1]), c, -mc));
+            pk0[i] = pack_bf16x2(a, b);
+            if (i & 1) s2 += a, s3 += b; else s0 += a, s1 += b;
+        }
+#pragma unroll
+        for (int i = 0; i < (NC - 32) / 2; ++i) {
+            const float a = fast_ex2(fmaf(__uint_as_float(v1[2 * i]), c, -mc)), b = fast_ex2(fmaf(__uint_as_float(v1[2 * i + 1]), c, -mc));
+            pk1[i] = pack_bf16x2(a, b);
+            if (i & 1) s2 += a, s3 += b; else s0 += a, s1 += b;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float a = (2 * i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v0[2 * i]), c, -mc)) : 0.f;
+            const float b = (2 * i + 1 < nvalid) ? fast_ex2(fmaf(__uint_as_float(v0[2 * i + 1]), c, -mc)) : 0.f;
+            pk0[i] = pack_bf16x2(a, b);
+            s0 += a, s1 += b;
+        }
+#pragma unroll
+        for (int i = 0; i < (NC - 32) / 2; ++i) {
+            const float a = (32 + 2 * i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v1[2 * i]), c, -mc)) : 0.f;
+            const float b = (32 + 2 * i + 1 < nvalid) ? fast_ex2(fmaf(__uint_as_float(v1[2 * i + 1]), c, -mc)) : 0.f;
+            pk1[i] = pack_bf16x2(a, b);
+            s2 += a, s3 += b;
+        }
     }
-    return (s0 + s1) + (s2 + s3);
+    tmem_st_x16(s_buf + (cbeg >> 1), pk0);
+    if constexpr (NC == 64)
+        tmem_st_x16(s_buf + (cbeg >> 1) + 16, pk1);
+    else
+        tmem_st_x8(s_buf + (cbeg >> 1) + 16, pk1);
+    const float sum = (s0 + s1) + (s2 + s3);
+    sSumU[part * 128 + row] = sum;
+    m_out = m;
+    sum_out = sum;
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -126,9 +183,9 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
                                 int H, int n_items) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
-    float* sMax = reinterpret_cast<float*>(smem + 2 * F_STAGE);  // [2][2][128]
-    float* sSum = sMax + 512;                                    // [2][2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 512);
+    float* sMax = reinterpret_cast<float*>(smem + 2 * F_STAGE);  // [2][4][128]
+    float* sSum = sMax + F_EXCH_FLOATS;                          // [2][4][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + F_EXCH_FLOATS);
     uint64_t *full = bars, *empty = bars + 2, *s_ready = bars + 4, *p_ready = bars + 6, *o_ready = bars + 8, *o_free = bars + 9;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
 
@@ -194,10 +251,8 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
                 if (elect_one()) {
                     const uint32_t vlo = (smem_lo + ((s * F_STAGE + 2 * OPER_BYTES) >> 4)) | LBO_MN;
 #pragma unroll
-                    for (int k = 0; k < 13; ++k) {
-                        const uint32_t acol = t * ROWS + (k < 7 ? k * 8 : 112 + (k - 7) * 8);  // keys [0,112) then [112,208)
-                        umma_bf16_ts(tmem_base + F_COL_O, tmem_base + acol, make_desc(vlo + k * 128, DESC_HI), idesc_o, k > 0);
-                    }
+                    for (int k = 0; k < 13; ++k)  // 16 keys per step = 8 packed columns
+                        umma_bf16_ts(tmem_base + F_COL_O, tmem_base + t * ROWS + k * 8, make_desc(vlo + k * 128, DESC_HI), idesc_o, k > 0);
                     umma_commit(o_ready);
                     if (t == 1) umma_commit(&empty[s]);  // both tiles of the item are done with this smem stage
                 }
@@ -221,84 +276,39 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
         }
     } else {
         // =========================== softmax / epilogue warps ===========================
-        const int quarter = warp & 3, hf = warp >> 2;
+        const int quarter = warp & 3, part = warp >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const float c = 0.125f * LOG2E;
-        const int cbeg = hf == 0 ? 0 : 112;
-        const int nsub = hf == 0 ? 7 : 6;  // 16-column sub-chunks owned by this warp
+        const int cbeg = part == 0 ? 0 : 16 + 48 * part;  // 0, 64, 112, 160
         float m_prev = 0.f, sum_prev = 0.f;
         for (int u = 0; u <= U; ++u) {
             float m_cur = 0.f, sum_cur = 0.f;
             if (u < U) {
                 const int t = u & 1;
-                const uint32_t s_addr = lane_addr + t * ROWS + cbeg;
                 mbar_wait(&s_ready[t], (u >> 1) & 1, 64);
                 tc_fence_after();
-                uint32_t va[16], vb2[16];
-                // ---- pass 1: row max over this warp's columns (next sub-chunk's TMEM load in flight) ----
-                float m = -INFINITY;
-                tmem_ld_32x32b_x16(s_addr, va);
-#pragma unroll
-                for (int s = 0; s < 7; ++s) {
-                    if (s < nsub) {
-                        tmem_ld_wait();
-                        const int nvalid = L - (cbeg + s * 16);
-                        if ((s & 1) == 0) {
-                            reg_fence(va);
-                            if (s + 1 < nsub) tmem_ld_32x32b_x16(s_addr + (s + 1) * 16, vb2);
-                            m = max16(va, m, nvalid);
-                        } else {
-                            reg_fence(vb2);
-                            if (s + 1 < nsub) tmem_ld_32x32b_x16(s_addr + (s + 1) * 16, va);
-                            m = max16(vb2, m, nvalid);
-                        }
-                    }
-                }
-                sMax[(t * 2 + hf) * 128 + row] = m;
-                tmem_ld_32x32b_x16(s_addr, va);  // first sub-chunk of pass 2, in flight across the exchange
-                named_bar_sync(1 + quarter, 64);   // the two warps sharing this lane quarter
-                m = fmaxf(m, sMax[(t * 2 + (hf ^ 1)) * 128 + row]);  // L >= 1: column 0 is valid, so m is finite
-                const float mc = m * c;
-                // ---- pass 2: p = exp2(s c - m c), packed to bf16 pairs in place ----
-                float sum = 0.f;
-#pragma unroll
-                for (int s = 0; s < 7; ++s) {
-                    if (s < nsub) {
-                        tmem_ld_wait();
-                        const int nvalid = L - (cbeg + s * 16);
-                        uint32_t pk[8];
-                        if ((s & 1) == 0) {
-                            reg_fence(va);
-                            if (s + 1 < nsub) tmem_ld_32x32b_x16(s_addr + (s + 1) * 16, vb2);
-                            sum += exp16(va, pk, c, mc, nvalid);
-                        } else {
-                            reg_fence(vb2);
-                            if (s + 1 < nsub) tmem_ld_32x32b_x16(s_addr + (s + 1) * 16, va);
-                            sum += exp16(vb2, pk, c, mc, nvalid);
-                        }
-                        tmem_st_x8(s_addr + s * 8, pk);
-                    }
-                }
-                sSum[(t * 2 + hf) * 128 + row] = sum;
+                if (part == 0)
+                    softmax_part<64>(lane_addr + t * ROWS, cbeg, L - cbeg, c, sMax + t * 512, sSum + t * 512, part, row, quarter, m_cur, sum_cur);
+                else
+                    softmax_part<48>(lane_addr + t * ROWS, cbeg, L - cbeg, c, sMax + t * 512, sSum + t * 512, part, row, quarter, m_cur, sum_cur);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_ready[t]);
-                m_cur = m;
-                sum_cur = sum;
             }
             if (u >= 1) {
-                // ---- read out O of unit u-1 (its P V ran while this warp did the softmax of unit u) ----
+                // ---- read out O of unit u-1 (its P V ran while the softmax of unit u was computed) ----
                 const int v = u - 1, t = v & 1;
                 const int it = blockIdx.x + (v >> 1) * gridDim.x;
                 const int b = it / H, hd = it - b * H;
                 mbar_wait(o_ready, v & 1, 65);
                 tc_fence_after();
-                named_bar_sync(1 + quarter, 64);  // partner's partial sum is visible
-                const float tot = sum_prev + sSum[(t * 2 + (hf ^ 1)) * 128 + row];
-                uint32_t o[32];
-                tmem_ld_32x32b_x32(lane_addr + F_COL_O + hf * 32, o);
+                uint32_t o[16];
+                tmem_ld_32x32b_x16(lane_addr + F_COL_O + part * 16, o);
+                // o_ready implies every warp arrived on p_ready(v), i.e. wrote its partial sum before (release / acquire chain)
+                const float* sS = sSum + t * 512;
+                const float tot = (sS[row] + sS[128 + row]) + (sS[256 + row] + sS[384 + row]);
                 tmem_ld_wait();
                 reg_fence(o);
                 tc_fence_before();
@@ -306,8 +316,20 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
                 if (lane == 0) mbar_arrive(o_free);
                 const int q = t * 128 + row;
                 if (q < L) {
-                    store_32cols_bf16(out + ((int64_t)b * L + q) * E + hd * HD + hf * 32, o, 1.f / tot);
-                    if (hf == 0 && lse_out != nullptr) lse_out[((int64_t)b * H + hd) * L + q] = m_prev * 0.125f + __logf(tot);
+                    const float inv = 1.f / tot;
+                    uint4 w0, w1;
+                    w0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                    w0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                    w0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                    w0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                    w1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                    w1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                    w1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                    w1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                    uint4* dst = reinterpret_cast<uint4*>(out + ((int64_t)b * L + q) * E + hd * HD + part * 16);
+                    dst[0] = w0;
+                    dst[1] = w1;
+                    if (part == 0 && lse_out != nullptr) lse_out[((int64_t)b * H + hd) * L + q] = m_prev * 0.125f + __logf(tot);
                 }
             }
             m_prev = m_cur;
@@ -354,19 +376,28 @@ constexpr int B_STAGE = 4 * OPER_BYTES;  // Q, K, V, dO
 constexpr int B_TAIL = 6144;             // lse / delta staging + barriers; also absorbs the 48-row over-read of the last tile
 constexpr int B_SMEM = 2 * B_STAGE + B_TAIL + 1024;
 constexpr uint32_t OFF_Q = 0, OFF_K = OPER_BYTES >> 4, OFF_V = (2 * OPER_BYTES) >> 4, OFF_DO = (3 * OPER_BYTES) >> 4;  // 16-B units
-constexpr uint32_t B_COL_ACC = 256;
+constexpr uint32_t B_COL_ACC = 384;
+constexpr int GROUP_WARPS = 8;
+constexpr int B_WARP_TMA = 16, B_WARP_MMA1 = 17, B_WARP_MMA2 = 18;
+constexpr int B_THREADS = 19 * 32;
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(B_THREADS, 1)
 attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                                 const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int L, int H,
-                                int n_items) {
+                                int n_items, long long* __restrict__ dbg) {
+    // dbg (development only, normally nullptr): clock64 stamps of chunks [32, 96) of CTA 0, 16 slots per chunk
+#define VB_STAMP(g, slot)                                                                                   \
+    do {                                                                                                    \
+        if (dbg != nullptr && blockIdx.x == 0 && (g) >= 32 && (g) < 96) dbg[((g)-32) * 16 + (slot)] = clock64(); \
+    } while (0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     float* sL = reinterpret_cast<float*>(smem + 2 * B_STAGE);  // [2][256] lse * log2(e); +inf for q >= L
     float* sD = sL + 512;                                      // [2][256] delta / 8;     0 for q >= L
     uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 512);
-    uint64_t *full = bars, *empty = bars + 2, *s_ready = bars + 4, *p_ready = bars + 6, *acc_ready = bars + 8, *acc_free = bars + 10;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t *full = bars, *empty = bars + 2, *s_ready = bars + 4, *p_ready = bars + 7, *c_free = bars + 10, *acc_ready = bars + 13,
+             *acc_free = bars + 14;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
@@ -375,20 +406,23 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
     const int n_local = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int G = 16 * n_local;  // column chunks: 4 units x 4 chunks per item
 
-    if (warp == WARP_TMA && elect_one()) {
+    if (warp == B_WARP_TMA && elect_one()) {
         tma_prefetch_desc(&tmQKV);
         tma_prefetch_desc(&tmDO);
     }
-    if (warp == WARP_MMA) {
+    if (warp == B_WARP_MMA1) {
         if (elect_one()) {
             for (int i = 0; i < 2; ++i) {
-                mbar_init(&full[i], 1);
+                mbar_init(&full[i], 2);  // TMA transaction bytes + the producer warp's lse / delta staging
                 mbar_init(&empty[i], 1);
-                mbar_init(&s_ready[i], 1);
-                mbar_init(&p_ready[i], MATH_WARPS);
-                mbar_init(&acc_ready[i], 1);
-                mbar_init(&acc_free[i], MATH_WARPS);
             }
+            for (int i = 0; i < 3; ++i) {
+                mbar_init(&s_ready[i], 1);
+                mbar_init(&p_ready[i], GROUP_WARPS);
+                mbar_init(&c_free[i], 1);
+            }
+            mbar_init(acc_ready, 1);
+            mbar_init(acc_free, GROUP_WARPS);
             fence_barrier_init();
         }
         __syncwarp();
@@ -399,9 +433,10 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t smem_lo = smem_u32(smem) >> 4;
 
-    if (warp == WARP_TMA) {
-        // =========================== TMA producer ===========================
+    if (warp == B_WARP_TMA) {
+        // =========================== TMA producer (+ lse / delta staging) ===========================
         for (int n = 0; n < n_local; ++n) {
             const int it = blockIdx.x + n * gridDim.x;
             const int b = it / H, hd = it - b * H;
@@ -420,17 +455,31 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
                 }
             }
             __syncwarp();
+            float lv[8], dv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = lane + 32 * i;
+                lv[i] = q < L ? __ldg(lse + (int64_t)it * L + q) : INFINITY;
+                dv[i] = q < L ? __ldg(delta + (int64_t)it * L + q) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sL[s * 256 + lane + 32 * i] = lv[i] * LOG2E;
+                sD[s * 256 + lane + 32 * i] = dv[i] * 0.125f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
         }
-    } else if (warp == WARP_MMA) {
-        // =========================== MMA issuer ===========================
-        // chunk g = 16 n + 4 unit + c. Order: MMA1(0) MMA1(1) | MMA2(g) MMA1(g+2) ... : the tensor pipe executes in issue
-        // order, so MMA1(g+2) may overwrite the chunk buffer as soon as MMA2(g) (which read the packed operands) is queued.
+    } else if (warp == B_WARP_MMA1) {
+        // =========================== MMA1 issuer: S_c, dP_c three chunks ahead of the math ===========================
+        // chunk g = 16 n + 4 unit + c goes to chunk buffer g % 3, free again once MMA2(g-3) (other issuer) has completed.
         const uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0), idesc16 = make_idesc_bf16(128, 16, 0, 0);
-        const uint32_t idesc2 = make_idesc_bf16(128, HD, 0, 1);
-        const uint32_t smem_lo = smem_u32(smem) >> 4;
-        auto issue_mma1 = [&](int g) {
-            const int n = g >> 4, un = (g >> 2) & 3, c = g & 3, s = n & 1, cb = g & 1;
+        int cb = 0;
+        uint32_t ph = 0;
+        for (int g = 0; g < G; ++g) {
+            const int n = g >> 4, un = (g >> 2) & 3, c = g & 3, s = n & 1;
             if ((g & 15) == 0) mbar_wait(&full[s], (n >> 1) & 1, 71);
+            mbar_wait(&c_free[cb], ph ^ 1, 79);  // passes at once for the first use of each buffer
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t base = smem_lo + ((s * B_STAGE) >> 4);
@@ -453,18 +502,26 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
                 umma_commit(&s_ready[cb]);
             }
             __syncwarp();
-        };
-        auto issue_mma2 = [&](int g) {
-            const int n = g >> 4, un = (g >> 2) & 3, c = g & 3, s = n & 1, cb = g & 1;
-            const int ug = g >> 2, ab = ug & 1;
-            mbar_wait(&p_ready[cb], (g >> 1) & 1, 72);
-            if (c == 0) mbar_wait(&acc_free[ab], ((ug >> 1) & 1) ^ 1, 73);  // accumulator of unit ug-2 has been read out
+            if (++cb == 3) cb = 0, ph ^= 1;
+        }
+    } else if (warp == B_WARP_MMA2) {
+        // =========================== MMA2 issuer: accumulate from the packed operands the math warps left in TMEM ===========================
+        const uint32_t idesc2 = make_idesc_bf16(128, HD, 0, 1);
+        int cb = 0;
+        uint32_t ph = 0;
+        for (int g = 0; g < G; ++g) {
+            const int n = g >> 4, un = (g >> 2) & 3, c = g & 3, s = n & 1;
+            const int ug = g >> 2;
+            if (lane == 0) VB_STAMP(g, 0);
+            mbar_wait(&p_ready[cb], ph, 72);
+            if (c == 0) mbar_wait(acc_free, (ug & 1) ^ 1, 73);  // accumulator of unit ug-1 has been read out
+            if (lane == 0) VB_STAMP(g, 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t base = smem_lo + ((s * B_STAGE) >> 4);
                 const uint32_t crow = c * 64 * 8;
                 const int ksteps = c == 3 ? 1 : 4;  // 16 operand rows per k-step
-                const uint32_t acc = tmem_base + B_COL_ACC + ab * 128;
+                const uint32_t acc = tmem_base + B_COL_ACC;
                 const uint32_t pbuf = tmem_base + cb * 128;
                 if (un < 2) {
                     const uint32_t kmn = (base + OFF_K + crow) | LBO_MN;  // dQ_t += dS_c K_c
@@ -482,65 +539,52 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
                             umma_bf16_ts(acc + 64, pbuf + 64 + acol, make_desc(qmn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));  // dK_j += dS^T Q_c
                         }
                 }
+                umma_commit(&c_free[cb]);  // chunk buffer reusable by MMA1(g+3)
                 if (c == 3) {
-                    umma_commit(&acc_ready[ab]);
-                    if (un == 3) umma_commit(&empty[s]);  // last MMA reading this item's smem stage
+                    umma_commit(acc_ready);
+                    // last MMA2 of the item; every MMA1 of the item completed before its math could run, so the stage is free
+                    if (un == 3) umma_commit(&empty[s]);
                 }
             }
             __syncwarp();
-        };
-        if (G > 0) {
-            issue_mma1(0);
-            issue_mma1(1);
-            for (int g = 0; g < G; ++g) {
-                issue_mma2(g);
-                if (g + 2 < G) issue_mma1(g + 2);
-            }
+            if (lane == 0) VB_STAMP(g, 2);
+            if (++cb == 3) cb = 0, ph ^= 1;
         }
     } else {
-        // =========================== math warps ===========================
-        const int quarter = warp & 3, hf = warp >> 2;
+        // =========================== math warps: group 0 takes even chunks, group 1 odd chunks + accumulator read-out ===========================
+        const int grp = warp >> 3;
+        const int quarter = warp & 3, hf = (warp >> 2) & 1;
         const int row = quarter * 32 + lane;
-        const int tid = threadIdx.x;  // 0..255: token index for the lse / delta staging
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const float c = 0.125f * LOG2E;
         const int c0 = hf * 32;
 
-        auto fetch_stats = [&](int n, float& l, float& d) {  // global loads for item n, staged into smem one item later
-            l = INFINITY;
-            d = 0.f;
-            if (n < n_local && tid < L) {
-                const int it = blockIdx.x + n * gridDim.x;
-                l = __ldg(lse + (int64_t)it * L + tid) * LOG2E;
-                d = __ldg(delta + (int64_t)it * L + tid) * 0.125f;
-            }
-        };
         auto readout = [&](int ug) {
-            const int ab = ug & 1, un = ug & 3;
+            const int un = ug & 3;
             const int it = blockIdx.x + (ug >> 2) * gridDim.x;
             const int b = it / H, hd = it - b * H;
-            mbar_wait(&acc_ready[ab], (ug >> 1) & 1, 74);
+            mbar_wait(acc_ready, ug & 1, 74);
             tc_fence_after();
             const int r = (un & 1) * 128 + row;  // query (dQ units) or key (dK/dV units)
             uint32_t a[32], a2[32];
             if (un < 2) {
-                tmem_ld_32x32b_x32(lane_addr + B_COL_ACC + ab * 128 + hf * 32, a);
+                tmem_ld_32x32b_x32(lane_addr + B_COL_ACC + hf * 32, a);
                 tmem_ld_wait();
                 reg_fence(a);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_free[ab]);
+                if (lane == 0) mbar_arrive(acc_free);
                 if (r < L) store_32cols_bf16(dqkv + ((int64_t)b * L + r) * ld3 + hd * HD + hf * 32, a, 1.f);
             } else {
-                // warps 0-3 drain dV, warps 4-7 drain dK (64 columns each)
-                tmem_ld_32x32b_x32(lane_addr + B_COL_ACC + ab * 128 + hf * 64, a);
-                tmem_ld_32x32b_x32(lane_addr + B_COL_ACC + ab * 128 + hf * 64 + 32, a2);
+                // column-half 0 warps drain dV, column-half 1 warps drain dK (64 columns each)
+                tmem_ld_32x32b_x32(lane_addr + B_COL_ACC + hf * 64, a);
+                tmem_ld_32x32b_x32(lane_addr + B_COL_ACC + hf * 64 + 32, a2);
                 tmem_ld_wait();
                 reg_fence(a);
                 reg_fence(a2);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_free[ab]);
+                if (lane == 0) mbar_arrive(acc_free);
                 if (r < L) {
                     bf16* dst = dqkv + ((int64_t)b * L + r) * ld3 + (hf == 0 ? 2 * E : E) + hd * HD;
                     store_32cols_bf16(dst, a, 1.f);
@@ -549,23 +593,20 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
             }
         };
 
-        float l_next, d_next;
-        fetch_stats(0, l_next, d_next);
-        sL[tid] = l_next;
-        sD[tid] = d_next;
-        fetch_stats(1, l_next, d_next);
-        named_bar_sync(5, 256);
-
         float lse_row = 0.f, dlt_row = 0.f;
-        for (int g = 0; g < G; ++g) {
-            const int n = g >> 4, un = (g >> 2) & 3, cc = g & 3, s = n & 1, cb = g & 1;
+        for (int g = grp; g < G; g += 2) {
+            const int n = g >> 4, un = (g >> 2) & 3, cc = g & 3, s = n & 1, cb = g % 3;
             const float* sLs = sL + s * 256;
             const float* sDs = sD + s * 256;
-            if (cc == 0 && un < 2) {
+            if ((g & 15) == grp) mbar_wait(&full[s], (n >> 1) & 1, 76);  // this group's first chunk of the item: lse / delta staged
+            if (cc < 2 && un < 2) {
                 lse_row = sLs[(un & 1) * 128 + row];
                 dlt_row = sDs[(un & 1) * 128 + row];
             }
-            mbar_wait(&s_ready[cb], (g >> 1) & 1, 75);
+            const bool stp = (warp & 7) == 0 && lane == 0;
+            if (stp) VB_STAMP(g, 5);
+            mbar_wait(&s_ready[cb], (g / 3) & 1, 75);
+            if (stp) VB_STAMP(g, 6);
             tc_fence_after();
             const uint32_t sbuf = lane_addr + cb * 128, dbuf = sbuf + 64;
             if (cc < 3) {
@@ -647,28 +688,23 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
                     tmem_st_x8(dbuf, pd);
                 }
             }
+            if (stp) VB_STAMP(g, 7);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[cb]);
-
-            if (cc == 0 && g >= 4) readout((g >> 2) - 1);  // previous unit's accumulator: its last MMA2 ran during this chunk
-            if ((g & 15) == 15) {
-                // item n is done with its lse / delta slot; stage item n+1's (fetched one item ago) and fetch item n+2's
-                sL[((n + 1) & 1) * 256 + tid] = l_next;
-                sD[((n + 1) & 1) * 256 + tid] = d_next;
-                fetch_stats(n + 2, l_next, d_next);
-                named_bar_sync(5, 256);
-            }
+            if (stp) VB_STAMP(g, 8);
+            if (cc == 3) readout(g >> 2);  // (group 1 only: cc == 3 is an odd chunk) the other group keeps the pipes busy meanwhile
+            if (stp) VB_STAMP(g, 9);
         }
-        if (G > 0) readout((G >> 2) - 1);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == WARP_MMA) {
+    if (warp == B_WARP_MMA1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+#undef VB_STAMP
 }
 
 template <typename K>
@@ -721,7 +757,24 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
     VB_CHECK_LAUNCH();
     const int n_items = batch * H;
     const int grid = n_items < num_sms() ? n_items : num_sms();
-    attention_bwd_persistent_kernel<<<grid, THREADS, B_SMEM, stream>>>(tmQKV, tmDO, lse, delta, dqkv, L, H, n_items);
+    static const bool dbg_on = getenv("VITB200_DBG_TIMING") != nullptr;  // development only
+    if (dbg_on) {
+        long long* dbg = nullptr;
+        VB_CHECK_CUDA(cudaMallocManaged(&dbg, 64 * 16 * sizeof(long long)));
+        VB_CHECK_CUDA(cudaMemset(dbg, 0, 64 * 16 * sizeof(long long)));
+        attention_bwd_persistent_kernel<<<grid, B_THREADS, B_SMEM, stream>>>(tmQKV, tmDO, lse, delta, dqkv, L, H, n_items, dbg);
+        VB_CHECK_CUDA(cudaStreamSynchronize(stream));
+        const long long t0 = dbg[0];
+        printf("[bwd timing] j: mma{waitP< waitP> mma2> mma1>} - math{waitS< waitS> math> arrive> readout>}\n");
+        for (int g = 0; g < 64; ++g) {
+            printf("[bwd timing] %3d:", g + 32);
+            for (int i = 0; i < 10; ++i) printf(" %7lld", dbg[g * 16 + i] ? dbg[g * 16 + i] - t0 : -1);
+            printf("\n");
+        }
+        cudaFree(dbg);
+        return VB_OK;
+    }
+    attention_bwd_persistent_kernel<<<grid, B_THREADS, B_SMEM, stream>>>(tmQKV, tmDO, lse, delta, dqkv, L, H, n_items, nullptr);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
