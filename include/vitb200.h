@@ -55,7 +55,10 @@ enum vb_epilogue {
     VB_EPI_BF16_DGELU = 3, /* out = acc * gelu_erf'(aux)                           aux = z: bf16 [M,N]      */
     VB_EPI_F32 = 4,        /* out = acc (+ bias)                                   out: f32 [M,N]           */
     VB_EPI_F32_ADD = 5,    /* out += acc   (TMA reduce-add; split_k >= 1)          out: f32 [M,N]           */
-    VB_EPI_SUMSQ = 6       /* sumsq[row / rows_per_sample, col / cols_per_group] += acc^2 ; nothing stored  */
+    VB_EPI_SUMSQ = 6,      /* sumsq[row / rows_per_sample, col / cols_per_group] += acc^2 ; nothing stored  */
+    VB_EPI_BF16_GELU_GRAD = 7, /* z = acc (+ bias); out = gelu_erf(z); out2 = gelu_erf'(z)  (training forward of fc1:
+                                  the derivative is saved instead of z, so the backward epilogue is one multiply) */
+    VB_EPI_BF16_MULAUX = 8 /* out = acc * aux                                      aux: bf16 [M,N] (= gelu'(z))     */
 };
 
 typedef struct vb_gemm_args {
@@ -72,7 +75,7 @@ typedef struct vb_gemm_args {
     int64_t ld_aux;
     void* out;          /* bf16 or f32 [M,N] (unused for SUMSQ) */
     int64_t ld_out;
-    void* out2;         /* bf16 [M,N], GELU only */
+    void* out2;         /* bf16 [M,N], GELU (may be NULL: z not stored) and GELU_GRAD only */
     int64_t ld_out2;
     float* sumsq;       /* f32 [n_samples, n_groups], SUMSQ only (accumulated into; caller zeroes) */
     int32_t rows_per_sample;

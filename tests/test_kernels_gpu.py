@@ -110,6 +110,19 @@ def test_gemm_gelu_two_outputs():
     _report("gemm_gelu.z", z, zref, atol=2e-2, rtol=1e-2)
     # activation must be gelu of the *stored* (bf16-rounded) pre-activation
     _report("gemm_gelu.a", act, torch.nn.functional.gelu(z.float()), atol=1e-3, rtol=1e-2)
+    # training variant: out2 = gelu'(z) (exact-erf derivative), out = gelu(z) of the fp32 pre-activation
+    gp = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_BF16_GELU_GRAD, bias=bias, out=act, out2=gp)
+    torch.cuda.synchronize()
+    zf = zref.clone().requires_grad_(True)
+    g = torch.nn.functional.gelu(zf)
+    g.sum().backward()
+    _report("gemm_gelu_grad.a", act, g.detach(), atol=2e-2, rtol=1e-2)
+    _report("gemm_gelu_grad.dg", gp, zf.grad, atol=1e-2, rtol=1e-2)
+    # inference variant: no second output
+    L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_BF16_GELU, bias=bias, out=act)
+    torch.cuda.synchronize()
+    _report("gemm_gelu_single.a", act, torch.nn.functional.gelu(zref), atol=2e-2, rtol=1e-2)
 
 
 def test_gemm_dgrad_mn_major_b_with_dgelu():
@@ -128,6 +141,10 @@ def test_gemm_dgrad_mn_major_b_with_dgelu():
     zf = z.float().requires_grad_(True)
     torch.nn.functional.gelu(zf).backward(ref)
     _report("dgrad_dgelu", out, zf.grad, atol=3e-2, rtol=1e-2)
+    # saved-derivative variant: out = acc * aux
+    L.gemm(dy, w, m=tokens, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out)
+    torch.cuda.synchronize()
+    _report("dgrad_mulaux", out, ref * z.float(), atol=3e-2, rtol=1e-2)
 
 
 @pytest.mark.parametrize("tokens,n_out,k_in,split_k", [(256, 128, 256, 1), (1000, 768, 768, 3), (197 * 8, 2304, 768, 4), (333, 136, 200, 2)])

@@ -25,6 +25,8 @@ EPI_BF16_DGELU = 3
 EPI_F32 = 4
 EPI_F32_ADD = 5
 EPI_SUMSQ = 6
+EPI_BF16_GELU_GRAD = 7
+EPI_BF16_MULAUX = 8
 
 
 class GemmArgs(Structure):

@@ -191,12 +191,24 @@ colsum_bf16_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ 
     const int r1 = min(r0 + rows_per_block, rows);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (col < cols) {
-        for (int r = r0 + warp; r < r1; r += 8) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)r * ldx + col));
+        auto add8 = [&](const uint4& u) {
             const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
             acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
             acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+        };
+        const bf16* base = x + col;
+        int r = r0 + warp;
+        for (; r + 24 < r1; r += 32) {  // four independent 128-bit loads in flight per thread
+            const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * ldx));
+            const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(r + 8) * ldx));
+            const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(r + 16) * ldx));
+            const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(r + 24) * ldx));
+            add8(u0);
+            add8(u1);
+            add8(u2);
+            add8(u3);
         }
+        for (; r < r1; r += 8) add8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * ldx)));
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];

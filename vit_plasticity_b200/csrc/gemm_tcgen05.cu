@@ -41,6 +41,7 @@ struct GemmKernelParams {
     long long ld_aux;
     float* sumsq;
     int rows_per_sample, cols_per_group, n_groups;
+    int has_out2;
 };
 
 struct WorkItem {
@@ -197,7 +198,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int hf = ew >> 2;   // which 128-column half of the tile
         uint8_t* stg = staging_base + ew * STAGING_BYTES;
         const int epi = p.epi;
-        const bool has_aux = (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU);
+        const bool has_aux = (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX);
         int acc = 0;
         uint32_t acc_phase = 0;
         int buf = 0;
@@ -236,7 +237,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (p.bias != nullptr && epi != VB_EPI_F32_ADD && epi != VB_EPI_SUMSQ && epi != VB_EPI_BF16_DGELU) {
+                    if (p.bias != nullptr && epi != VB_EPI_F32_ADD && epi != VB_EPI_SUMSQ && epi != VB_EPI_BF16_DGELU && epi != VB_EPI_BF16_MULAUX) {
                         if (col0 + 32 <= p.N) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
@@ -294,6 +295,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 const float2 z = unpack_bf16x2(ax[j]);
                                 o[j] = pack_bf16x2(f[2 * j] * dgelu_erf(z.x), f[2 * j + 1] * dgelu_erf(z.y));
                             }
+                        } else if (epi == VB_EPI_BF16_MULAUX) {
+                            const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 g = unpack_bf16x2(ax[j]);
+                                o[j] = pack_bf16x2(f[2 * j] * g.x, f[2 * j + 1] * g.y);
+                            }
+                        } else if (epi == VB_EPI_BF16_GELU_GRAD) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float g0, d0, g1, d1;
+                                gelu_and_grad_erf(f[2 * j], g0, d0);
+                                gelu_and_grad_erf(f[2 * j + 1], g1, d1);
+                                o[j] = pack_bf16x2(g0, g1);
+                                o2[j] = pack_bf16x2(d0, d1);
+                            }
                         } else if (epi == VB_EPI_BF16_GELU) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
@@ -308,7 +325,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
                         }
-                        const bool two = (epi == VB_EPI_BF16_GELU);
+                        const bool two = (epi == VB_EPI_BF16_GELU || epi == VB_EPI_BF16_GELU_GRAD) && p.has_out2;
                         uint8_t* b0 = stg + (two ? 0 : buf * 2048);
                         if (elect_one()) {
                             if (two)
@@ -402,13 +419,13 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     VB_CHECK_ARG(a->a && a->b, "vb_gemm_bf16: null operand");
     VB_CHECK_ARG(a->a_layout == 0 || a->a_layout == 1, "vb_gemm_bf16: bad a_layout %d", a->a_layout);
     VB_CHECK_ARG(a->b_layout == 0 || a->b_layout == 1, "vb_gemm_bf16: bad b_layout %d", a->b_layout);
-    VB_CHECK_ARG(a->epilogue >= VB_EPI_BF16 && a->epilogue <= VB_EPI_SUMSQ, "vb_gemm_bf16: bad epilogue %d",
+    VB_CHECK_ARG(a->epilogue >= VB_EPI_BF16 && a->epilogue <= VB_EPI_BF16_MULAUX, "vb_gemm_bf16: bad epilogue %d",
                  a->epilogue);
     VB_CHECK_ARG(a->n % 8 == 0, "vb_gemm_bf16: n=%d must be a multiple of 8", a->n);
     const int epi = a->epilogue;
     const int split_k = a->split_k < 1 ? 1 : a->split_k;
     VB_CHECK_ARG(split_k == 1 || epi == VB_EPI_F32_ADD, "vb_gemm_bf16: split_k > 1 needs VB_EPI_F32_ADD");
-    if (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU)
+    if (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX)
         VB_CHECK_ARG(a->aux != nullptr && a->ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,
                      "vb_gemm_bf16: aux must be non-null, 16B aligned, ld multiple of 8");
     if (epi == VB_EPI_SUMSQ)
@@ -417,7 +434,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
                      "vb_gemm_bf16: SUMSQ needs sumsq, rows_per_sample, cols_per_group %% 128 == 0, n_groups");
     else
         VB_CHECK_ARG(a->out != nullptr, "vb_gemm_bf16: null out");
-    if (epi == VB_EPI_BF16_GELU) VB_CHECK_ARG(a->out2 != nullptr, "vb_gemm_bf16: GELU epilogue needs out2");
+    if (epi == VB_EPI_BF16_GELU_GRAD) VB_CHECK_ARG(a->out2 != nullptr, "vb_gemm_bf16: GELU_GRAD epilogue needs out2");
     if (a->bias) VB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "vb_gemm_bf16: bias must be 16B aligned");
 
     CUtensorMap tmA, tmB, tmC, tmC2;
@@ -448,7 +465,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
         rc = make_tensor_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->out, a->n, a->m, a->ld_out * 2, 32, 32,
                                 CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
-        if (epi == VB_EPI_BF16_GELU) {
+        if ((epi == VB_EPI_BF16_GELU || epi == VB_EPI_BF16_GELU_GRAD) && a->out2 != nullptr) {
             rc = make_tensor_map_2d(&tmC2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->out2, a->n, a->m, a->ld_out2 * 2, 32,
                                     32, CU_TENSOR_MAP_SWIZZLE_64B);
             if (rc) return rc;
@@ -475,6 +492,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     p.rows_per_sample = a->rows_per_sample;
     p.cols_per_group = a->cols_per_group;
     p.n_groups = a->n_groups;
+    p.has_out2 = a->out2 != nullptr;
 
     if (a->a_layout == 0 && a->b_layout == 0) return launch_gemm<0, 0>(tmA, tmB, tmC, tmC2, p, stream);
     if (a->a_layout == 0 && a->b_layout == 1) return launch_gemm<0, 1>(tmA, tmB, tmC, tmC2, p, stream);

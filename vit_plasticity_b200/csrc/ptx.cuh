@@ -269,6 +269,15 @@ __device__ __forceinline__ float dgelu_erf(float z) {
     return fmaf(z * 0.3989422804014327f, e, cdf);
 }
 
+// gelu(z) and gelu'(z) together: one MUFU.RCP + one MUFU.EX2, four FP32 ops more than gelu alone
+__device__ __forceinline__ void gelu_and_grad_erf(float z, float& g, float& dg) {
+    float h, e;
+    half_erfc_exp(z, h, e);
+    g = fmaf(-fabsf(z), h, fmaxf(z, 0.f));
+    const float cdf = z >= 0.f ? 1.0f - h : h;
+    dg = fmaf(z * 0.3989422804014327f, e, cdf);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

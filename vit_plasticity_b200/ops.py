@@ -72,13 +72,15 @@ def _wgrad_split_k(n_out: int, k_in: int, tokens: int) -> int:
 # --------------------------------------------------------------------------------------------------
 # functional building blocks (no autograd); x / dy are bf16 [tokens, features], contiguous
 # --------------------------------------------------------------------------------------------------
-def linear_fwd(x, w16, bias, *, residual=None, gelu=False):
+def linear_fwd(x, w16, bias, *, residual=None, gelu=False, gelu_grad=False):
+    """y = x W^T + b with the epilogue fused. ``gelu``: returns (gelu(z), z); ``gelu_grad``: returns (gelu(z), gelu'(z)) —
+    the training path saves the derivative instead of the pre-activation, so fc2's dgrad epilogue is one multiply."""
     m, k = x.shape
     n = w16.shape[0]
     out = torch.empty(m, n, device=x.device, dtype=torch.bfloat16)
-    if gelu:
+    if gelu or gelu_grad:
         z = torch.empty(m, n, device=x.device, dtype=torch.bfloat16)
-        L.gemm(x, w16, m=m, n=n, k=k, epilogue=L.EPI_BF16_GELU, bias=bias, out=out, out2=z)
+        L.gemm(x, w16, m=m, n=n, k=k, epilogue=L.EPI_BF16_GELU_GRAD if gelu_grad else L.EPI_BF16_GELU, bias=bias, out=out, out2=z)
         return out, z
     if residual is not None:
         L.gemm(x, w16, m=m, n=n, k=k, epilogue=L.EPI_BF16_RESID, bias=bias, aux=residual, out=out)
@@ -87,12 +89,15 @@ def linear_fwd(x, w16, bias, *, residual=None, gelu=False):
     return out
 
 
-def linear_dgrad(dy, w16, *, dgelu_z=None):
-    """dx = dy @ W (W stored [n_out, k_in], used as-is as an MN-major B operand); optional * gelu'(z)."""
+def linear_dgrad(dy, w16, *, dgelu_z=None, mul=None):
+    """dx = dy @ W (W stored [n_out, k_in], used as-is as an MN-major B operand); optional * gelu'(z) computed from a saved
+    z (``dgelu_z``) or * a saved derivative (``mul``)."""
     m, n_out = dy.shape
     k_in = w16.shape[1]
     dx = torch.empty(m, k_in, device=dy.device, dtype=torch.bfloat16)
-    if dgelu_z is not None:
+    if mul is not None:
+        L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=mul, out=dx)
+    elif dgelu_z is not None:
         L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_DGELU, aux=dgelu_z, out=dx)
     else:
         L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16, out=dx)
@@ -162,9 +167,9 @@ def _attn_bwd(dout, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need, ba
 
 
 def _mlp_fwd(h, w116, b1, w216, b2, residual):
-    a, z = linear_fwd(h, w116, b1, gelu=True)
+    a, gp = linear_fwd(h, w116, b1, gelu_grad=True)  # gp = gelu'(fc1 pre-activation)
     out = linear_fwd(a, w216, b2, residual=residual)
-    return out, z, a
+    return out, gp, a
 
 
 def _mlp_bwd(dout, h, z, a, w116, w216, w1_shape, w2_shape, need):
@@ -173,7 +178,7 @@ def _mlp_bwd(dout, h, z, a, w116, w216, w1_shape, w2_shape, need):
     db2 = bias_grad(dout) if need[4] else None
     if not (need[0] or need[1] or need[2]):
         return None, None, None, dw2, db2
-    dz = linear_dgrad(dout, w216, dgelu_z=z)  # gelu'(z) fused into the fc2 dgrad epilogue
+    dz = linear_dgrad(dout, w216, mul=z)  # z holds gelu'(pre-activation), saved by the forward epilogue
     dw1 = linear_wgrad(dz, h, w1_shape) if need[1] else None
     db1 = bias_grad(dz) if need[2] else None
     dh = linear_dgrad(dz, w116) if need[0] else None
@@ -300,9 +305,9 @@ class MlpFn(Function):
 class BlockFn(Function):
     """Pre-norm transformer block: out = x' + mlp(ln2(x')), x' = x + attn(ln1(x)).
 
-    Saved for backward (bf16): x, ln1(x), qkv, attention output, x', ln2(x'), fc1 pre-activation, gelu output,
+    Saved for backward (bf16): x, ln1(x), qkv, attention output, x', ln2(x'), gelu'(fc1 pre-activation), gelu output,
     plus fp32 mean/rstd/lse. Nothing else touches HBM: bias, GELU and both residual adds live in GEMM epilogues,
-    gelu' in the fc2-dgrad epilogue, and each residual-gradient add in the LayerNorm backward kernel.
+    the gelu' multiply in the fc2-dgrad epilogue, and each residual-gradient add in the LayerNorm backward kernel.
     """
 
     @staticmethod
