@@ -4,7 +4,11 @@
 Stated tolerances (bf16 storage / fp32 accumulate vs the reference's fp32):
   logits        relative L2 error <= 2e-2   (observed bf16-vs-fp32 max abs 0.02 on ~1-magnitude logits)
   loss          abs <= 2e-2
-  gradients     per-tensor relative L2 error <= 4e-2, total grad-norm within 2e-2 relative
+  gradients     per-tensor relative L2 error <= 4e-2 over the FULL tensor (tiny / small fixtures hold full tensors; for
+                ViT-B/16 the full tensors are compared with the CPU oracle in test_against_cpu_oracle_same_inputs);
+                total grad-norm within 2e-2 relative. The ViT-B/16 fixture holds 256 strided samples + the norm per
+                tensor: that sampled estimate of the same relative error has ~±15 % estimator noise on top of the
+                2-3.5 % bf16 error of the deepest fc1 / qkv weights, so it is held to 6e-2.
   plasticity    independent pairs: ratios within 2e-2 relative (attention), 5e-3 (LayerNorm / fc1 / fc2)
 """
 
@@ -113,7 +117,7 @@ def test_logits_loss_grads_match_reference(name):
         assert e_log <= 2e-2, f"{name}/{fs}: logits rel L2 {e_log:.3e}"
         assert abs(float(loss) - ref["loss"]) <= 2e-2
         assert abs(gnorm - ref["grad_norm"]) <= 2e-2 * ref["grad_norm"], f"grad norm {gnorm} vs {ref['grad_norm']}"
-        worst = max(check_summary(g, ref["grads"][k], 4e-2, f"{name}/{fs}/{k}") for k, g in grads.items())
+        worst = max(check_summary(g, ref["grads"][k], 4e-2 if "full" in ref["grads"][k] else 6e-2, f"{name}/{fs}/{k}") for k, g in grads.items())
         REPORT[f"{name}/{fs}"]["worst_grad_rel_l2"] = worst
     _dump_report()
 
@@ -124,15 +128,17 @@ def _freeze_inner(model, comps):
     freeze_model(model, comps)
 
 
-@pytest.mark.parametrize("name", ["tiny", "small"])
+@pytest.mark.parametrize("name", ["tiny", "small", "vit_base"])
 def test_against_cpu_oracle_same_inputs(name):
-    """Same check against the oracle run here on the host (different seeds than the fixture)."""
+    """Same check against the oracle run here on the host (different seeds than the fixture); full tensors, ViT-B/16
+    included (4 images: a few seconds of fp32 CPU work)."""
     gold = load(name)
     arch = arch_of(gold)
     sd = O.init_state_dict(arch, seed=7)
     model = build(name, gold, arch, sd)
-    x = O.synthetic_images(5, arch, 21)
-    y = O.synthetic_labels(5, arch, 22)
+    nb = 4 if name == "vit_base" else 5
+    x = O.synthetic_images(nb, arch, 21)
+    y = O.synthetic_labels(nb, arch, 22)
     o_loss, o_logits, o_grads = O.loss_and_grads(sd, x, y, arch)
     model.train()
     logits = model(x.to(DEV))
@@ -140,8 +146,13 @@ def test_against_cpu_oracle_same_inputs(name):
     loss.backward()
     assert rel_l2(logits, o_logits) <= 2e-2
     assert abs(float(loss) - float(o_loss)) <= 2e-2
-    for k, p in model.named_parameters():
-        assert rel_l2(p.grad, o_grads[k]) <= 4e-2, k
+    prefix = "model." if name == "vit_base" else ""
+    errs = {k: rel_l2(p.grad, o_grads[k[len(prefix):]]) for k, p in model.named_parameters()}
+    REPORT[f"{name}/oracle_full_tensor"] = {"worst_grad_rel_l2": max(errs.values()), "worst_tensor": max(errs, key=errs.get),
+                                            "logits_rel_l2": rel_l2(logits, o_logits)}
+    _dump_report()
+    for k, e in errs.items():
+        assert e <= 4e-2, f"{k}: {e:.3e}"
 
 
 @pytest.mark.parametrize("name", ["tiny", "small", "vit_base"])
