@@ -100,11 +100,119 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma
     }
 }
 
-// Backward: persistent warps, gamma in shared memory, x / dy / dres of the NEXT row prefetched while the current row
-// is reduced; dgamma / dbeta partials live in registers across the row loop.
+// Backward: persistent warps, gamma in shared memory, dgamma / dbeta partials in registers across the row loop.
+// Two CTAs (16 warps) per SM, <= 128 registers: each warp has the 9 independent 128-bit loads of its row in flight and
+// the other 15 warps cover their latency (the earlier one-CTA/SM version with a register-prefetched next row reached
+// 62 % of the HBM peak). Normalised x and gamma*dy are recomputed in the second sweep instead of being kept.
+template <int CHUNKS>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
+                     bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols) {
+    __shared__ float red[LN_WARPS][32 * 8 + 1];
+    __shared__ float sgamma[CHUNKS * 256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = cols >> 3;
+    for (int i = threadIdx.x; i < CHUNKS * 256; i += LN_WARPS * 32) sgamma[i] = i < cols ? __ldg(gamma + i) : 0.f;
+    __syncthreads();
+    float dg[CHUNKS][8], db[CHUNKS][8];
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+    const float inv_cols = 1.f / (float)cols;
+    const int stride = gridDim.x * LN_WARPS;
+    for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += stride) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * cols);
+        const uint4* dyr = reinterpret_cast<const uint4*>(dy + (size_t)row * cols);
+        const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + (size_t)row * cols) : nullptr;
+        uint4 cx[CHUNKS], cd[CHUNKS], cr[CHUNKS];
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            const bool ok = c < nchunks;
+            cx[i] = ok ? __ldg(xr + c) : make_uint4(0, 0, 0, 0);
+            cd[i] = ok ? __ldg(dyr + c) : make_uint4(0, 0, 0, 0);
+            cr[i] = (ok && drr) ? __ldg(drr + c) : make_uint4(0, 0, 0, 0);
+        }
+        const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            const uint32_t wx[4] = {cx[i].x, cx[i].y, cx[i].z, cx[i].w};
+            const uint32_t wd[4] = {cd[i].x, cd[i].y, cd[i].z, cd[i].w};
+            const float4 g0 = *reinterpret_cast<const float4*>(sgamma + c * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(sgamma + c * 8 + 4);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const bool ok = c < nchunks;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 fx = unpack_bf16x2(wx[j]);
+                const float2 fd = unpack_bf16x2(wd[j]);
+                const float h0 = ok ? (fx.x - mu) * rs : 0.f, h1 = ok ? (fx.y - mu) * rs : 0.f;
+                dg[i][2 * j] += fd.x * h0;
+                dg[i][2 * j + 1] += fd.y * h1;
+                db[i][2 * j] += fd.x;
+                db[i][2 * j + 1] += fd.y;
+                const float y0 = fd.x * g[2 * j], y1 = fd.y * g[2 * j + 1];
+                s1 += y0 + y1;
+                s2 += y0 * h0 + y1 * h1;
+            }
+        }
+        s1 = warp_sum(s1) * inv_cols;
+        s2 = warp_sum(s2) * inv_cols;
+        uint4* dxr = reinterpret_cast<uint4*>(dx + (size_t)row * cols);
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+                const uint32_t wx[4] = {cx[i].x, cx[i].y, cx[i].z, cx[i].w};
+                const uint32_t wd[4] = {cd[i].x, cd[i].y, cd[i].z, cd[i].w};
+                const uint32_t wr[4] = {cr[i].x, cr[i].y, cr[i].z, cr[i].w};
+                const float4 g0 = *reinterpret_cast<const float4*>(sgamma + c * 8);
+                const float4 g1 = *reinterpret_cast<const float4*>(sgamma + c * 8 + 4);
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 fx = unpack_bf16x2(wx[j]);
+                    const float2 fd = unpack_bf16x2(wd[j]);
+                    const float2 fr = unpack_bf16x2(wr[j]);  // zeros when there is no residual gradient
+                    const float h0 = (fx.x - mu) * rs, h1 = (fx.y - mu) * rs;
+                    o[j] = pack_bf16x2(rs * (fd.x * g[2 * j] - s1 - h0 * s2) + fr.x, rs * (fd.y * g[2 * j + 1] - s1 - h1 * s2) + fr.y);
+                }
+                dxr[c] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    if (dgamma == nullptr && dbeta == nullptr) return;  // frozen norm: parameter gradients not needed
+    // block reduction of the per-warp partials, one chunk-slot at a time, then one atomic per column
+    for (int pass = 0; pass < 2; ++pass) {
+        float* out = pass == 0 ? dgamma : dbeta;
+        if (out == nullptr) continue;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? dg[i][j] : db[i][j];
+            __syncthreads();
+            const int t = threadIdx.x;  // 256 threads <-> 256 columns of this slot
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < LN_WARPS; ++w) s += red[w][t];
+            const int col = (i * 32 + (t >> 3)) * 8 + (t & 7);
+            if (col < cols) atomicAdd(out + col, s);
+        }
+    }
+}
+
+// Backward for wide rows (cols > 768, e.g. ViT-L/H): one CTA per SM (the per-lane dgamma / dbeta partials alone take
+// 16 registers per 256 columns), so x / dy / dres of the NEXT row are prefetched into registers while the current row is
+// reduced.
 template <int CHUNKS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+layernorm_bwd_wide_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
                      bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols) {
     __shared__ float red[LN_WARPS][32 * 8 + 1];
@@ -337,9 +445,15 @@ extern "C" int vb_layernorm_bwd(const void* dy, const void* x, const float* gamm
     int grid = (rows + LN_WARPS - 1) / LN_WARPS;
     const int max_grid = num_sms() * 2;
     if (grid > max_grid) grid = max_grid;
-    VB_LN_DISPATCH(chunks, (layernorm_bwd_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(
-                               static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd,
-                               static_cast<const bf16*>(dres), static_cast<bf16*>(dx), dgamma, dbeta, rows, cols)));
+    if (chunks <= 3) {
+        VB_LN_DISPATCH(chunks, (layernorm_bwd_kernel < C <= 3 ? C : 1 > <<<grid, LN_WARPS * 32, 0, stream>>>(
+                                   static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd,
+                                   static_cast<const bf16*>(dres), static_cast<bf16*>(dx), dgamma, dbeta, rows, cols)));
+    } else {
+        VB_LN_DISPATCH(chunks, (layernorm_bwd_wide_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(
+                                   static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd,
+                                   static_cast<const bf16*>(dres), static_cast<bf16*>(dx), dgamma, dbeta, rows, cols)));
+    }
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
