@@ -221,6 +221,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             };
             load_aux(aux_cur, colbase);  // issued before the accumulator wait: latency hides behind the MMA
+            if (has_aux && w + (int)gridDim.x < total_work) {
+                // The aux rows of this CTA's NEXT tile go to L2 now: a whole main loop ahead of their use, so the
+                // per-chunk loads above hit L2 (~300 cycles) instead of HBM (~1500), which had made the short-K
+                // residual / GELU' epilogues latency-bound (proj forward: 136 us against 93 us without epilogue).
+                const WorkItem nx = decode_work(p, w + gridDim.x);
+                const int nrow = nx.m_blk * BM + q * 32 + lane, ncol = nx.n_blk * BN + hf * 128;
+                if (nrow < p.M && ncol < p.N) {
+                    const bf16* pa = p.aux + (long long)nrow * p.ld_aux + ncol;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+                    if (ncol + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 64));
+                }
+            }
 
             mbar_wait(&tfull_bar[acc], acc_phase, 4);
             tc_fence_after();
