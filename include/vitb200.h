@@ -116,6 +116,11 @@ int vb_attention_bwd(const void* qkv, const void* out, const void* dout, const f
  * delta = attn(qkv_a) - attn(qkv_b), subtracted in fp32 before the bf16 down-cast. */
 int vb_attention_pair_delta(const void* qkv_a, const void* qkv_b, int64_t ld_qkv, void* delta, int64_t ld_delta,
                             int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
+/* All layers of the estimator in one launch (architecture.py:877-881 feeds the same embedding to every block):
+ * qkv_a / qkv_b hold every layer's projection side by side, [batch*seq, ld_qkv] with feature = layer*3E + which*E +
+ * head*d + j; delta: bf16 [layers, batch*seq, E]. seq <= 208. */
+int vb_attention_pair_delta_layers(const void* qkv_a, const void* qkv_b, int64_t ld_qkv, void* delta, int32_t layers,
+                                   int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / data-movement helpers on the path

@@ -274,6 +274,27 @@ def test_attention_pair_delta():
     _report("attn_pair", delta, ref, atol=2e-2, rtol=2e-2)
 
 
+@pytest.mark.parametrize("layers,batch,seq,heads", [(3, 5, 197, 12), (2, 3, 5, 2), (1, 150, 197, 4)])
+def test_attention_pair_delta_all_layers(layers, batch, seq, heads):
+    """One launch over every layer's slice of the concatenated qkv projections (the estimator's layout)."""
+    L = _lib()
+    hd = 64
+    e = heads * hd
+    qa = _rand(batch * seq, layers * 3 * e, seed=1).bfloat16()
+    qb = _rand(batch * seq, layers * 3 * e, seed=2).bfloat16()
+    delta = L.attention_pair_delta_layers(qa, qb, layers, batch, seq, heads, hd)
+    torch.cuda.synchronize()
+    assert delta.shape == (layers, batch * seq, e)
+    for i in range(layers):
+        sl = slice(i * 3 * e, (i + 1) * 3 * e)
+        ref = _attn_ref(qa[:, sl], batch, seq, heads, hd)[0] - _attn_ref(qb[:, sl], batch, seq, heads, hd)[0]
+        _report(f"attn_pair_layers[{i}]", delta[i], ref, atol=2e-2, rtol=2e-2)
+    # identical inputs cancel exactly (fp32 subtraction of identical accumulators)
+    zero = L.attention_pair_delta_layers(qa, qa, layers, batch, seq, heads, hd)
+    torch.cuda.synchronize()
+    assert float(zero.float().abs().max()) == 0.0
+
+
 # ---------------------------------------------------------------------------------------------------
 # Element-wise helpers
 # ---------------------------------------------------------------------------------------------------

@@ -84,6 +84,10 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
     ),
+    "vb_attention_pair_delta_layers": (
+        c_int32,
+        [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    ),
     "vb_cast_f32_to_bf16": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vb_cast_bf16_to_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vb_im2col_patches": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
@@ -270,6 +274,17 @@ def attention_pair_delta(qkv_a, qkv_b, delta, batch, seq, heads, head_dim):
         lib().vb_attention_pair_delta(qkv_a.data_ptr(), qkv_b.data_ptr(), qkv_a.stride(0), delta.data_ptr(), delta.stride(0), batch, seq, heads, head_dim, _stream()),
         "vb_attention_pair_delta",
     )
+
+
+def attention_pair_delta_layers(qkv_a, qkv_b, layers, batch, seq, heads, head_dim):
+    """[layers, batch*seq, E] bf16: attn(qkv_a) - attn(qkv_b) for every layer's slice of the concatenated projections."""
+    assert qkv_a.stride(0) == qkv_b.stride(0) and qkv_a.stride(1) == 1 and qkv_b.stride(1) == 1
+    delta = torch.empty(layers, batch * seq, heads * head_dim, device=qkv_a.device, dtype=torch.bfloat16)
+    _check(
+        lib().vb_attention_pair_delta_layers(qkv_a.data_ptr(), qkv_b.data_ptr(), qkv_a.stride(0), delta.data_ptr(), layers, batch, seq, heads, head_dim, _stream()),
+        "vb_attention_pair_delta_layers",
+    )
+    return delta
 
 
 # --------------------------------------------------------------------------------------------------

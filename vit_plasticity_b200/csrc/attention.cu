@@ -443,6 +443,8 @@ int launch_attention_fwd_tc2(const bf16* qkv, bf16* out, float* lse, int batch, 
 int launch_attention_fwd_tc3(const bf16* qkv, bf16* out, float* lse, int batch, int L, int H, cudaStream_t stream);
 int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                              int batch, int L, int H, cudaStream_t stream);
+int launch_attention_pair_tc3(const bf16* qkv_a, const bf16* qkv_b, int64_t ld, bf16* delta, int layers, int batch, int L, int H,
+                              cudaStream_t stream);
 int launch_attention_bwd_tc2(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                              int batch, int L, int H, cudaStream_t stream);  // attention_tc2.cu: 2 CTAs/SM, P/dS in TMEM
 
@@ -487,8 +489,32 @@ extern "C" int vb_attention_pair_delta(const void* qkv_a, const void* qkv_b, int
     VB_CHECK_ARG(head_dim == HD, "vb_attention_pair_delta: head_dim must be 64 (got %d)", head_dim);
     VB_CHECK_ARG(batch > 0 && heads > 0 && seq > 0 && seq <= 208, "vb_attention_pair_delta: seq=%d must be in [1, 208]", seq);
     VB_CHECK_ARG(ld_qkv % 8 == 0 && ld_delta % 8 == 0, "vb_attention_pair_delta: leading dims must be multiples of 8");
+    if (attn_impl() == 3 && ld_delta == (int64_t)heads * HD)
+        return launch_attention_pair_tc3(static_cast<const bf16*>(qkv_a), static_cast<const bf16*>(qkv_b), ld_qkv,
+                                         static_cast<bf16*>(delta), 1, batch, seq, heads, stream);
     return launch_fwd<13, true>(static_cast<const bf16*>(qkv_a), static_cast<const bf16*>(qkv_b), ld_qkv,
                                 static_cast<bf16*>(delta), ld_delta, nullptr, batch, seq, heads, stream);
+}
+
+extern "C" int vb_attention_pair_delta_layers(const void* qkv_a, const void* qkv_b, int64_t ld_qkv, void* delta, int32_t layers,
+                                              int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream_) {
+    using namespace vb;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(qkv_a && qkv_b && delta, "vb_attention_pair_delta_layers: null pointer");
+    VB_CHECK_ARG(head_dim == HD, "vb_attention_pair_delta_layers: head_dim must be 64 (got %d)", head_dim);
+    VB_CHECK_ARG(layers > 0 && batch > 0 && heads > 0 && seq > 0 && seq <= 208, "vb_attention_pair_delta_layers: seq=%d must be in [1, 208]", seq);
+    const int64_t E = (int64_t)heads * HD;
+    VB_CHECK_ARG(ld_qkv % 8 == 0 && ld_qkv >= layers * 3 * E, "vb_attention_pair_delta_layers: ld_qkv=%lld must be a multiple of 8, >= layers * 3E",
+                 (long long)ld_qkv);
+    if (attn_impl() == 3)
+        return launch_attention_pair_tc3(static_cast<const bf16*>(qkv_a), static_cast<const bf16*>(qkv_b), ld_qkv,
+                                         static_cast<bf16*>(delta), layers, batch, seq, heads, stream);
+    for (int i = 0; i < layers; ++i) {  // development fallback (VITB200_ATTN=...): one legacy launch per layer
+        int rc = launch_fwd<13, true>(static_cast<const bf16*>(qkv_a) + i * 3 * E, static_cast<const bf16*>(qkv_b) + i * 3 * E, ld_qkv,
+                                      static_cast<bf16*>(delta) + (int64_t)i * batch * seq * E, E, nullptr, batch, seq, heads, stream);
+        if (rc) return rc;
+    }
+    return VB_OK;
 }
 
 extern "C" int64_t vb_attention_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads) {

@@ -178,9 +178,16 @@ __device__ __forceinline__ void softmax_part(uint32_t s_buf, int cbeg, int nvali
     sum_out = sum;
 }
 
+// PAIR = false: out = attention(qkv), lse written (training forward).
+// PAIR = true (plasticity estimator): every item is run on two inputs, tmQKV (a) then tmQKV2 (b), and
+// out = attention(a) - attention(b), subtracted in fp32 (the normalised rows of a wait in registers) before the single
+// bf16 rounding. Items then also range over `layers`: the qkv tensors hold all layers' projections side by side
+// (feature = layer * 3E + which * E + head * 64) and out is [layers][batch * L][E].
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
-attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out, int L,
-                                int H, int n_items) {
+attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKV2,
+                                bf16* __restrict__ out, float* __restrict__ lse_out, int L, int H, int batch, int n_items) {
+    constexpr int SUBS = PAIR ? 2 : 1;  // smem stages / TMEM units are per (item, input)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     float* sMax = reinterpret_cast<float*>(smem + 2 * F_STAGE);  // [2][4][128]
@@ -192,10 +199,13 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
     const int E = H * HD;
-    const int n_local = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_local = SUBS * ((n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);  // (item, input) stages
     const int U = 2 * n_local;  // units (query tiles) this CTA processes
 
-    if (warp == WARP_TMA && elect_one()) tma_prefetch_desc(&tmQKV);
+    if (warp == WARP_TMA && elect_one()) {
+        tma_prefetch_desc(&tmQKV);
+        if (PAIR) tma_prefetch_desc(&tmQKV2);
+    }
     if (warp == WARP_MMA) {
         if (elect_one()) {
             for (int i = 0; i < 2; ++i) {
@@ -220,8 +230,9 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
     if (warp == WARP_TMA) {
         // =========================== TMA producer ===========================
         for (int n = 0; n < n_local; ++n) {
-            const int it = blockIdx.x + n * gridDim.x;
-            const int b = it / H, hd = it - b * H;
+            const int it = blockIdx.x + (n / SUBS) * gridDim.x;
+            const int hd = it % H, b = (it / H) % batch, layer = it / (H * batch);
+            const CUtensorMap* tm = (PAIR && (n & 1)) ? &tmQKV2 : &tmQKV;
             const int s = n & 1;
             mbar_wait(&empty[s], ((n >> 1) & 1) ^ 1, 60);
             if (elect_one()) {
@@ -231,7 +242,7 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
                 for (int op = 0; op < 3; ++op)
 #pragma unroll
                     for (int h2 = 0; h2 < 2; ++h2)
-                        tma_load_3d(st + op * OPER_BYTES + h2 * BOX_ROWS * 128, &tmQKV, &full[s], op * E + hd * HD, h2 * BOX_ROWS, b);
+                        tma_load_3d(st + op * OPER_BYTES + h2 * BOX_ROWS * 128, tm, &full[s], (layer * 3 + op) * E + hd * HD, h2 * BOX_ROWS, b);
             }
             __syncwarp();
         }
@@ -282,6 +293,7 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
         const float c = 0.125f * LOG2E;
         const int cbeg = part == 0 ? 0 : 16 + 48 * part;  // 0, 64, 112, 160
         float m_prev = 0.f, sum_prev = 0.f;
+        float okeep[PAIR ? 2 : 1][16];  // PAIR: normalised output rows of input a, per query tile, until input b's arrive
         for (int u = 0; u <= U; ++u) {
             float m_cur = 0.f, sum_cur = 0.f;
             if (u < U) {
@@ -300,8 +312,8 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
             if (u >= 1) {
                 // ---- read out O of unit u-1 (its P V ran while the softmax of unit u was computed) ----
                 const int v = u - 1, t = v & 1;
-                const int it = blockIdx.x + (v >> 1) * gridDim.x;
-                const int b = it / H, hd = it - b * H;
+                const int it = blockIdx.x + ((v >> 1) / SUBS) * gridDim.x;
+                const int hd = it % H, b = (it / H) % batch, layer = it / (H * batch);
                 mbar_wait(o_ready, v & 1, 65);
                 tc_fence_after();
                 uint32_t o[16];
@@ -315,21 +327,35 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16*
                 __syncwarp();
                 if (lane == 0) mbar_arrive(o_free);
                 const int q = t * 128 + row;
-                if (q < L) {
-                    const float inv = 1.f / tot;
+                const float inv = 1.f / tot;
+                float r[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(o[i]) * inv;
+                bool store = q < L;
+                if (PAIR) {
+                    if (((v >> 1) & 1) == 0) {  // input a: keep, nothing to store yet
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) okeep[t][i] = r[i];
+                        store = false;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = okeep[t][i] - r[i];
+                    }
+                }
+                if (store) {
                     uint4 w0, w1;
-                    w0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-                    w0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-                    w0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-                    w0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-                    w1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-                    w1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-                    w1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-                    w1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-                    uint4* dst = reinterpret_cast<uint4*>(out + ((int64_t)b * L + q) * E + hd * HD + part * 16);
+                    w0.x = pack_bf16x2(r[0], r[1]);
+                    w0.y = pack_bf16x2(r[2], r[3]);
+                    w0.z = pack_bf16x2(r[4], r[5]);
+                    w0.w = pack_bf16x2(r[6], r[7]);
+                    w1.x = pack_bf16x2(r[8], r[9]);
+                    w1.y = pack_bf16x2(r[10], r[11]);
+                    w1.z = pack_bf16x2(r[12], r[13]);
+                    w1.w = pack_bf16x2(r[14], r[15]);
+                    uint4* dst = reinterpret_cast<uint4*>(out + (((int64_t)layer * batch + b) * L + q) * E + hd * HD + part * 16);
                     dst[0] = w0;
                     dst[1] = w1;
-                    if (part == 0 && lse_out != nullptr) lse_out[((int64_t)b * H + hd) * L + q] = m_prev * 0.125f + __logf(tot);
+                    if (!PAIR && part == 0 && lse_out != nullptr) lse_out[((int64_t)b * H + hd) * L + q] = m_prev * 0.125f + __logf(tot);
                 }
             }
             m_prev = m_cur;
@@ -733,11 +759,33 @@ int launch_attention_fwd_tc3(const bf16* qkv, bf16* out, float* lse, int batch, 
     int rc = make_maps(&tmQKV, qkv, nullptr, nullptr, batch, L, H);
     if (rc) return rc;
     static bool done = false;
-    rc = set_smem(attention_fwd_persistent_kernel, F_SMEM, done);
+    rc = set_smem(attention_fwd_persistent_kernel<false>, F_SMEM, done);
     if (rc) return rc;
     const int n_items = batch * H;
     const int grid = n_items < num_sms() ? n_items : num_sms();
-    attention_fwd_persistent_kernel<<<grid, THREADS, F_SMEM, stream>>>(tmQKV, out, lse, L, H, n_items);
+    attention_fwd_persistent_kernel<false><<<grid, THREADS, F_SMEM, stream>>>(tmQKV, tmQKV, out, lse, L, H, batch, n_items);
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+// delta[layer][batch * L][E] = attention(qkv_a) - attention(qkv_b); qkv_*: [batch * L, ld] with ld >= layers * 3E
+int launch_attention_pair_tc3(const bf16* qkv_a, const bf16* qkv_b, int64_t ld, bf16* delta, int layers, int batch, int L, int H,
+                              cudaStream_t stream) {
+    using namespace attn3;
+    CUtensorMap tmA, tmB;
+    const int64_t E = (int64_t)H * HD;
+    int rc = make_tensor_map_3d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv_a, (uint64_t)layers * 3 * E, L, batch, ld * 2, (uint64_t)L * ld * 2, 64,
+                                BOX_ROWS, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tensor_map_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv_b, (uint64_t)layers * 3 * E, L, batch, ld * 2, (uint64_t)L * ld * 2, 64,
+                            BOX_ROWS, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    static bool done = false;
+    rc = set_smem(attention_fwd_persistent_kernel<true>, F_SMEM, done);
+    if (rc) return rc;
+    const int n_items = layers * batch * H;
+    const int grid = n_items < num_sms() ? n_items : num_sms();
+    attention_fwd_persistent_kernel<true><<<grid, THREADS, F_SMEM, stream>>>(tmA, tmB, delta, nullptr, L, H, batch, n_items);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }

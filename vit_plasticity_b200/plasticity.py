@@ -122,12 +122,16 @@ class PlasticityEstimator:
             q = torch.empty(m, nl * 3 * e, device=dev, dtype=torch.bfloat16)
             L.gemm(t, self.w_qkv, m=m, n=nl * 3 * e, k=e, epilogue=L.EPI_BF16, bias=self.b_qkv, out=q)
             qkv.append(q)
-        delta = torch.empty(m, e, device=dev, dtype=torch.bfloat16)
+        if seq <= 208:
+            delta_all = L.attention_pair_delta_layers(qkv[0], qkv[1], nl, n, seq, heads, e // heads)  # one launch, all layers
+        else:
+            delta_all = torch.empty(nl, m, e, device=dev, dtype=torch.bfloat16)
+            for i in range(nl):
+                qa, qb = qkv[0][:, i * 3 * e : (i + 1) * 3 * e], qkv[1][:, i * 3 * e : (i + 1) * 3 * e]
+                L.attention_pair_delta(qa, qb, delta_all[i], n, seq, heads, e // heads)
         for i in range(nl):
-            qa, qb = qkv[0][:, i * 3 * e : (i + 1) * 3 * e], qkv[1][:, i * 3 * e : (i + 1) * 3 * e]
-            L.attention_pair_delta(qa, qb, delta, n, seq, heads, e // heads)
             # sumsq pointer offset by i with n_groups = n_layers writes column i of ss_attn
-            L.gemm(delta, self.w_out[i], m=m, n=e, k=e, epilogue=L.EPI_SUMSQ, sumsq=ss_attn[:, i:], rows_per_sample=seq, cols_per_group=e, n_groups=nl)
+            L.gemm(delta_all[i], self.w_out[i], m=m, n=e, k=e, epilogue=L.EPI_SUMSQ, sumsq=ss_attn[:, i:], rows_per_sample=seq, cols_per_group=e, n_groups=nl)
         # ---- assemble in the reference's key order ----
         rows = [ss_emb[:, 0]]
         for i in range(nl):
