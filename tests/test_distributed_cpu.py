@@ -121,3 +121,34 @@ def test_env_contract_without_torchrun(monkeypatch):
         assert isinstance(model, nn.Linear)  # single process: no wrapper, as in the reference
     with pytest.raises(NotImplementedError):
         D.build_manager({"device": "cpu", "tp": 2, "dp": 1})
+
+
+def _gather_worker(rank, world, port, outdir):
+    import numpy as np
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vit_plasticity_b200.distributed import shard_range
+    from vit_plasticity_b200.plasticity import gather_tables
+
+    n_total, rows = 11, 4
+    lo, hi = shard_range(n_total, rank, world)
+    # column j of the full table holds j in every row: the gathered table must be 0..n_total-1 in order
+    local = np.tile(np.arange(lo, hi, dtype=np.float32), (rows, 1))
+    table = gather_tables(local, n_total)
+    if rank == 0:
+        np.save(os.path.join(outdir, "table.npy"), table)
+    else:
+        assert table is None
+    dist.destroy_process_group()
+
+
+def test_sweep_gather_reassembles_shards_in_order(tmp_path):
+    """The sweep's only collective: rank-ordered contiguous shards come back as one table on rank 0."""
+    import numpy as np
+
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    table = np.load(tmp_path / "table.npy")
+    assert table.shape == (4, 11)
+    assert (table == np.arange(11, dtype=np.float32)).all()

@@ -239,6 +239,37 @@ def test_plasticity_matches_reference(name):
     _dump_report()
 
 
+def test_perturbation_sweep_matches_oracle_and_is_shard_invariant():
+    """configs[4] driver on one GPU: ratios against the CPU oracle on the same (x, x + eps n) pairs; running the two
+    halves as the two ranks of a world-size-2 job gives the same table (noise is per image, shards are contiguous)."""
+    from vit_plasticity_b200.plasticity import PlasticityEstimator, perturbation_sweep
+
+    gold = load("small")
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    model = build("small", gold, arch, sd).eval()
+    n = 6
+    x = O.synthetic_images(n, arch, 31)
+    eps_list = [1.0, 0.1]
+    full = perturbation_sweep(model, x, eps_list, noise_seed=5, pairs_per_call=4)
+    noise = torch.stack([torch.randn(x.shape[1:], generator=torch.Generator().manual_seed(5 * 1_000_003 + i)) for i in range(n)])
+    for eps in eps_list:
+        ref = O.pair_distances(sd, x, x + eps * noise, arch)
+        for k, v in ref.items():
+            if k == "embedding":
+                continue
+            r_ref = v / ref["embedding"]
+            r = full[eps][k] / full[eps]["embedding"]
+            tol = 5e-2 if "attn" in k.split("_", 1)[1] or "norm" in k else 5e-3  # non-linear components lose digits as eps shrinks
+            assert np.max(np.abs(r - r_ref) / r_ref) <= tol, (eps, k, float(np.max(np.abs(r - r_ref) / r_ref)))
+    est = PlasticityEstimator(model)
+    halves = [perturbation_sweep(model, x, eps_list, noise_seed=5, pairs_per_call=4, rank=r, world=2, estimator=est) for r in range(2)]
+    for eps in eps_list:
+        for k in full[eps]:
+            both = np.concatenate([halves[0][eps][k], halves[1][eps][k]])
+            assert np.allclose(both, full[eps][k], rtol=1e-5, atol=0), (eps, k)
+
+
 def test_decomposition_and_probes_api_tiny():
     gold = load("tiny")
     arch = arch_of(gold)

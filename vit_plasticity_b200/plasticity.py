@@ -156,6 +156,60 @@ class PlasticityEstimator:
         return {k: table[j] for j, k in enumerate(self.keys())}
 
 
+def gather_tables(local: np.ndarray, n_total: int, group=None) -> np.ndarray | None:
+    """Concatenate the ranks' [rows, n_local] distance tables along the pair axis on rank 0 (contiguous shards in rank
+    order, see ``distributed.shard_range``). The only collective of the sweep: one gather at the end."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(local, parts, dst=0, group=group)
+    if rank != 0:
+        return None
+    table = np.concatenate(parts, axis=1)
+    assert table.shape[1] == n_total, (table.shape, n_total)
+    return table
+
+
+def perturbation_sweep(model, images, eps_list, noise_seed: int = 0, pairs_per_call: int = 64, rank: int | None = None,
+                       world: int | None = None, group=None, estimator: "PlasticityEstimator | None" = None):
+    """Plasticity under input perturbations of growing magnitude (BASELINE.json configs[4]): pairs (x, x + eps * n),
+    n ~ N(0, 1) drawn per image from ``noise_seed``, for every eps in ``eps_list``.
+
+    The N images are sharded contiguously over the ranks (each pair is independent: apps/vit/analysis.py:68 reduces per
+    sample); every rank streams its shard from ``images`` (host or device, fp32 NCHW) through the fused estimator and
+    only the (1 + 5 n_layers) x N_local distance table per eps leaves the GPU. No collective on the data path; rank 0
+    receives {eps: {key: (N,) float32}} from one gather per eps at the end, the other ranks get None.
+    """
+    from .distributed import shard_range
+
+    est = estimator if estimator is not None else PlasticityEstimator(model)
+    n_total = images.shape[0]
+    lo, hi = shard_range(n_total, rank, world)
+    dev = next(_inner(model).parameters()).device
+    tables = {float(e): [] for e in eps_list}
+    for s0 in range(lo, hi, pairs_per_call):
+        s1 = min(s0 + pairs_per_call, hi)
+        x = images[s0:s1].to(dev, non_blocking=True).float()
+        # per-image generators: the noise of image i does not depend on how the images are sharded or batched
+        noise = torch.stack([torch.randn(x.shape[1:], generator=torch.Generator().manual_seed(noise_seed * 1_000_003 + i)) for i in range(s0, s1)]).to(dev)
+        for e in eps_list:
+            tables[float(e)].append(est.squared_distances(x, x + float(e) * noise).sqrt())
+    out = {}
+    keys = est.keys()
+    for e, chunks in tables.items():
+        local = torch.cat(chunks, 1).cpu().numpy() if chunks else np.zeros((len(keys), 0), np.float32)
+        table = gather_tables(local, n_total, group)
+        out[e] = None if table is None else {k: table[j] for j, k in enumerate(keys)}
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_rank(group) != 0:
+        return None
+    return out
+
+
 def pair_distances(model, x1, x2) -> dict[str, np.ndarray]:
     return PlasticityEstimator(model).pair_distances(x1, x2)
 
