@@ -46,6 +46,31 @@ def parse():
     return ap.parse_args()
 
 
+def workload_config(model_name: str, batch: int, world: int, comps, n_trainable=None):
+    """The `config` object shared by both arms (the reference arm runs a bounded sample of the same workload)."""
+    cfg = {"workload": f"ViT-{model_name}/16 finetuning (fwd + CE + bwd + clip 1.0 + SGD 1e-2 m0.9), batch {batch}/GPU, 10-class synthetic CIFAR-10-shaped 224x224, random init",
+           "global_batch": batch * world, "parallelism": f"dp{world}", "freeze": comps}
+    if n_trainable is not None:
+        cfg["trainable_params"] = n_trainable
+    return cfg
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, averaged over the launches of the committed
+    `ncu --set full` capture of this command (profiles/*ncu_full_gemm*.txt); None if no capture is committed."""
+    files = sorted((ROOT / "profiles").glob("*ncu_full_gemm*.txt"))
+    if not files:
+        return None, None
+    tot, n = 0.0, 0
+    for line in files[-1].read_text().splitlines():
+        parts = line.split()
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            val, unit = float(parts[1]), parts[2]
+            tot += val * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
+            n += 1
+    return (tot / (n / 2) if n else None), files[-1].name
+
+
 def peaks():
     p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     f = ROOT / "MEASURED_PEAKS.json"
@@ -131,7 +156,7 @@ def run_reference(args):
         "impl": "reference", "metric": f"ViT-{args.model[0].upper()}/16 finetune img/s", "value": round(v, 3), "unit": "img/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ViT-{args.model}/16 full finetuning, batch 512/GPU, 10-class synthetic 224x224 (CPU arm: bounded sample, batch 8)", "freeze": comps},
+        "config": dict(workload_config(args.model, args.batch, max(1, args.gpus), comps), sample="CPU arm: bounded sample of the workload, 8 images per step"),
         "cpu_baseline": {"value": round(v, 3), "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -284,16 +309,18 @@ def main():
                "sample": f"oracle port (torch fp32) of the same step at batch 8 (of 512), 2 timed steps after 1 warm-up, {dt:.2f} s/step"}
 
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+    traffic, traffic_src = ncu_traffic_per_launch()
     step_flops = 3 * FWD_GFLOP_PER_IMG.get(args.model, 0) * 1e9 * B if not comps else None
     out = {
         "metric": f"ViT-{args.model[0].upper()}/16 finetune img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"ViT-{args.model}/16 finetuning (fwd + CE + bwd + clip 1.0 + SGD 1e-2 m0.9), batch {B}/GPU, 10-class synthetic CIFAR-10-shaped 224x224, random init",
-                   "global_batch": B * world, "parallelism": f"dp{world}", "freeze": comps, "trainable_params": n_trainable, "l2": "inputs>L2 (one step streams >30 GB)"},
+        "config": dict(workload_config(args.model, B, world, comps, n_trainable), l2="inputs>L2 (one step streams >30 GB)"),
         "e2e": e2e, "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1) if achieved else None, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": round(achieved / pk["bf16_tflops_sustained"], 4) if achieved else None, "traffic": None,
+                     "frac": round(achieved / pk["bf16_tflops_sustained"], 4) if achieved else None,
+                     "traffic": round(traffic) if traffic else None, "traffic_unit": "bytes per launch (mean over the launches of " + str(traffic_src) + ")" if traffic else None,
+                     "flops_per_launch": round(gemm_flops / max(1, len(gemm_events))), "us_per_launch": round(gemm_ms * 1e3 / max(1, len(gemm_events)), 2),
                      "kernel": "gemm_tcgen05_kernel (all fwd/dgrad/wgrad launches of the timed steps, CUDA events per launch)", "peak_source": pk["source"] + " bf16_tflops_sustained",
                      "gemm_share_of_step": round(gemm_ms / ms_total, 4), "gemm_launches": len(gemm_events),
                      "whole_step_frac": round(step_flops * args.steps / (ms_total / 1e3) / 1e12 / pk["bf16_tflops_sustained"], 4) if step_flops else None},
