@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--pairs", type=int, default=64, help="plasticity pairs per call (0 disables the secondary block)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--torch-sgd", action="store_true", help="clip_grad_norm_ + torch.optim.SGD instead of the fused arena step")
     return ap.parse_args()
 
 
@@ -194,7 +195,9 @@ def main():
     freeze_model(model, comps)
     n_trainable = sum(p.numel() for p in model.parameters() if p.requires_grad)
     dp = DataParallel(model) if world > 1 else None
-    opt = build_optimizer(model, "sgd", lr=1e-2, momentum=0.9)  # apps/vit/configs/cifar10.yaml
+    # apps/vit/configs/cifar10.yaml: SGD lr 1e-2 momentum 0.9, grad_clip 1 — as the fused clip+SGD step over the flat
+    # gradient arena (same arithmetic as clip_grad_norm_ + torch.optim.SGD; tests/test_model_gpu.py::test_fused_sgd_*)
+    opt = build_optimizer(dp or model, "sgd", lr=1e-2, momentum=0.9, fused=not args.torch_sgd)
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
     n_host = 2  # distinct pinned host batches, alternated

@@ -190,6 +190,60 @@ def test_train_step_matches_reference(name):
     _dump_report()
 
 
+@pytest.mark.parametrize("components", [[], ["emb", "attn_norm", "ffn_norm", "ffn_fc1", "ffn_fc2"]])
+def test_fused_sgd_matches_torch_sgd(components):
+    """FusedSGD (flat arena, in-place wgrad accumulation, one clip+momentum+update pass) against the reference sequence
+    clip_grad_norm_ + torch.optim.SGD on the same model, three steps incl. one with two accumulated micro-batches."""
+    from vit_plasticity_b200.finetune import FusedSGD, build_optimizer, freeze_model, train_step
+
+    gold = load("small")
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    models = [build("small", gold, arch, sd), build("small", gold, arch, sd)]
+    for m in models:
+        m.train()
+        freeze_model(m, components)
+    opts = [build_optimizer(models[0], "sgd", lr=1e-2, momentum=0.9), build_optimizer(models[1], "sgd", lr=1e-2, momentum=0.9, fused=True)]
+    assert isinstance(opts[1], FusedSGD)
+    xs = [O.synthetic_images(4, arch, 40 + i).to(DEV) for i in range(4)]
+    ys = [O.synthetic_labels(4, arch, 50 + i).to(DEV) for i in range(4)]
+    steps = [[(xs[0], ys[0])], [(xs[1], ys[1]), (xs[2], ys[2])], [(xs[3], ys[3])]]
+    for batches in steps:
+        out = [train_step(m, o, batches, grad_clip=1.0) for m, o in zip(models, opts)]
+        assert abs(float(out[0][0]) - float(out[1][0])) <= 1e-4 * max(1.0, abs(float(out[0][0])))
+        assert abs(float(out[0][1]) - float(out[1][1])) <= 1e-4 * float(out[0][1]), (float(out[0][1]), float(out[1][1]))
+    for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
+        assert rel_l2(b, a) <= 2e-5, (k, rel_l2(b, a))
+        if k.split(".")[0] == "embedding" and "emb" in components:
+            assert torch.equal(a.cpu(), sd[k]), k  # frozen parameters untouched
+    # gradients stay views of the arena (zeroed, not dropped)
+    arena = opts[1].arena
+    assert float(arena.abs().max()) == 0.0
+    assert all(p.grad is not None and p.grad.data_ptr() >= arena.data_ptr() for p in opts[1].trainable)
+
+
+def test_fused_sgd_train_step_matches_reference_fixture():
+    from vit_plasticity_b200.finetune import build_optimizer, train_step
+
+    gold = load("vit_base")
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    model = build("vit_base", gold, arch, sd)
+    ref = gold["train"]["full"]
+    x = O.synthetic_images(gold["batch"], arch, gold["x_seed"]).to(DEV)
+    y = O.synthetic_labels(gold["batch"], arch, gold["y_seed"]).to(DEV)
+    model.train()
+    opt = build_optimizer(model, "sgd", lr=1e-2, momentum=0.9, fused=True)
+    loss, gnorm = train_step(model, opt, [(x, y)], grad_clip=1.0)
+    assert abs(float(loss) - ref["loss"]) <= 2e-2
+    assert abs(float(gnorm) - ref["grad_norm"]) <= 2e-2 * ref["grad_norm"]
+    new = {k[len("model."):]: v for k, v in model.state_dict().items()}
+    worst = max(abs(float((new[k].cpu().double() - sd[k].double()).norm()) - dn) / (dn + 1e-30) for k, dn in ref["param_delta_norm"].items())
+    REPORT["vit_base/fused_sgd_worst_delta_norm_rel"] = worst
+    assert worst <= 5e-2
+    _dump_report()
+
+
 @pytest.mark.parametrize("name", ["tiny", "small", "vit_base"])
 def test_plasticity_matches_reference(name):
     from vit_plasticity_b200.plasticity import PlasticityEstimator, get_plasticity

@@ -75,38 +75,42 @@ class DataParallel(nn.Module):
         if not params:
             raise ValueError("DataParallel: the module has no trainable parameter")
         cap = max(1, int(bucket_mb * 1024 * 1024 // 4))
+        # One flat fp32 arena holds every trainable gradient (slots 16-byte aligned, in reverse registration order: the
+        # order backward produces them); the buckets are consecutive slices of it. finetune.FusedSGD steps straight from
+        # this arena, so the averaged gradients are never copied out.
+        pad4 = lambda n: (n + 3) // 4 * 4
+        order = list(reversed(params))
+        for p in order:
+            if p.dtype != torch.float32:
+                raise TypeError("DataParallel expects fp32 parameters")
+        self.arena = torch.zeros(sum(pad4(p.numel()) for p in order), device=order[0].device, dtype=torch.float32)
+        self.arena_offset: dict[torch.Tensor, int] = {}
         self.buckets: list[torch.Tensor] = []
         self._slot: dict[torch.Tensor, tuple[int, torch.Tensor]] = {}
         self._expected: list[int] = []
-        cur: list[torch.Tensor] = []
-        cur_n = 0
-
-        def close():
-            nonlocal cur, cur_n
-            if not cur:
-                return
-            flat = torch.zeros(cur_n, device=cur[0].device, dtype=torch.float32)
-            off = 0
-            for p in cur:
-                self._slot[p] = (len(self.buckets), flat[off : off + p.numel()].view_as(p))
-                off += p.numel()
-            self.buckets.append(flat)
-            self._expected.append(len(cur))
-            cur, cur_n = [], 0
-
-        for p in reversed(params):  # gradients become ready roughly in reverse registration order
-            if p.dtype != torch.float32:
-                raise TypeError("DataParallel expects fp32 parameters")
-            if cur and cur_n + p.numel() > cap:
-                close()
-            cur.append(p)
-            cur_n += p.numel()
-        close()
+        off = b_start = 0
+        n_in_bucket = 0
+        for p in order:
+            if n_in_bucket and off - b_start + p.numel() > cap:
+                self.buckets.append(self.arena[b_start:off])
+                self._expected.append(n_in_bucket)
+                b_start, n_in_bucket = off, 0
+            self.arena_offset[p] = off
+            self._slot[p] = (len(self.buckets), self.arena[off : off + p.numel()].view_as(p))
+            off += pad4(p.numel())
+            n_in_bucket += 1
+        self.buckets.append(self.arena[b_start:off])
+        self._expected.append(n_in_bucket)
         self._ready = [0] * len(self.buckets)
         self._handles: list = []
         self._launched = [False] * len(self.buckets)
         self.require_grad_sync = True
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        # kernels that accumulate straight into a persistent p.grad (ops.grad_target) bypass autograd's AccumulateGrad
+        # and therefore its hooks: they report completed gradients through this registry instead
+        from . import ops
+
+        ops.register_grad_ready_hook(self)
         # replicas must start identical: broadcast rank 0's parameters and buffers
         if self.world > 1:
             for t in list(module.parameters()) + list(module.buffers()):
@@ -123,6 +127,8 @@ class DataParallel(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _on_grad(self, p: torch.Tensor) -> None:
+        if p not in self._slot:
+            return
         b, slot = self._slot[p]
         if p.grad.data_ptr() != slot.data_ptr():
             slot.copy_(p.grad)

@@ -55,6 +55,38 @@ def shadow_bf16(p: torch.Tensor) -> torch.Tensor:
     return w16
 
 
+# --------------------------------------------------------------------------------------------------
+# in-place parameter gradients
+# --------------------------------------------------------------------------------------------------
+# When a parameter already owns a persistent fp32 ``.grad`` (a slot of finetune.FusedSGD's / DataParallel's flat arena,
+# zeroed once per step by one memset), the wgrad GEMM (TMA reduce-add), the column sums and the LayerNorm backward
+# accumulate straight into it and the autograd Function returns None for that input: no per-tensor zero fill, no
+# AccumulateGrad add, and the optimizer reads the arena directly.
+INPLACE_GRADS = True
+_grad_ready_hooks: list = []  # weakrefs to objects with ``_on_grad(param)`` (DataParallel)
+
+
+def register_grad_ready_hook(obj) -> None:
+    _grad_ready_hooks.append(weakref.ref(obj))
+
+
+def grad_target(p) -> torch.Tensor | None:
+    g = getattr(p, "grad", None)
+    if INPLACE_GRADS and g is not None and g.is_cuda and g.dtype == torch.float32 and g.shape == p.shape and g.is_contiguous():
+        return g
+    return None
+
+
+def grad_done(p) -> None:
+    """A gradient was accumulated in place: run the hooks AccumulateGrad would have run."""
+    for ref in list(_grad_ready_hooks):
+        obj = ref()
+        if obj is None:
+            _grad_ready_hooks.remove(ref)
+        else:
+            obj._on_grad(p)
+
+
 def _f32c(p: torch.Tensor | None) -> torch.Tensor | None:
     if p is None:
         return None
@@ -104,19 +136,37 @@ def linear_dgrad(dy, w16, *, dgelu_z=None, mul=None):
     return dx
 
 
-def linear_wgrad(dy, x, shape):
-    """dW = dy^T x in fp32 (split-K, TMA reduce-add into a zeroed buffer)."""
+def linear_wgrad(dy, x, shape, param=None):
+    """dW = dy^T x in fp32 (split-K, TMA reduce-add). Accumulates into ``param.grad`` when that is a persistent arena slot
+    (then returns None: autograd has nothing left to do), else into a fresh zeroed buffer that is returned."""
     tokens, n_out = dy.shape
     k_in = x.shape[1]
-    dw = torch.zeros(n_out, k_in, device=dy.device, dtype=torch.float32)
+    tgt = grad_target(param)
+    dw = tgt.view(n_out, k_in) if tgt is not None else torch.zeros(n_out, k_in, device=dy.device, dtype=torch.float32)
     L.gemm(dy, x, m=n_out, n=k_in, k=tokens, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=_wgrad_split_k(n_out, k_in, tokens))
+    if tgt is not None:
+        grad_done(param)
+        return None
     return dw.view(shape)
 
 
-def bias_grad(dy):
-    db = torch.zeros(dy.shape[1], device=dy.device, dtype=torch.float32)
+def bias_grad(dy, param=None):
+    tgt = grad_target(param)
+    db = tgt if tgt is not None else torch.zeros(dy.shape[1], device=dy.device, dtype=torch.float32)
     L.colsum_bf16(dy, db)
+    if tgt is not None:
+        grad_done(param)
+        return None
     return db
+
+
+def _ln_grad_buffers(gamma_p, beta_p, like, need_g, need_b):
+    """(dgamma buffer, dbeta buffer, in-place flags) for a LayerNorm backward call."""
+    tg = grad_target(gamma_p) if need_g else None
+    tb = grad_target(beta_p) if need_b else None
+    dg = tg if tg is not None else (torch.zeros_like(like) if need_g else None)
+    db = tb if tb is not None else (torch.zeros_like(like) if need_b else None)
+    return dg, db, tg is not None, tb is not None
 
 
 def _as_bf16_2d(t: torch.Tensor) -> torch.Tensor:
@@ -151,17 +201,17 @@ def _attn_fwd(h, wqkv16, bqkv, wo16, bo, residual, batch, seq, heads):
     return out, qkv, o, lse
 
 
-def _attn_bwd(dout, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need, batch, seq, heads):
-    """need = (dh, dWqkv, dbqkv, dWo, dbo)"""
+def _attn_bwd(dout, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need, batch, seq, heads, params=(None, None, None, None)):
+    """need = (dh, dWqkv, dbqkv, dWo, dbo); params = (Wqkv, bqkv, Wo, bo) Parameters for in-place gradient accumulation"""
     e = o.shape[1]
-    dwo = linear_wgrad(dout, o, wo_shape) if need[3] else None
-    dbo = bias_grad(dout) if need[4] else None
+    dwo = linear_wgrad(dout, o, wo_shape, params[2]) if need[3] else None
+    dbo = bias_grad(dout, params[3]) if need[4] else None
     if not (need[0] or need[1] or need[2]):
         return None, None, None, dwo, dbo
     do = linear_dgrad(dout, wo16)
     dqkv = L.attention_bwd(qkv, o, do, lse, batch, seq, heads, e // heads)
-    dwqkv = linear_wgrad(dqkv, h, wqkv_shape) if need[1] else None
-    dbqkv = bias_grad(dqkv) if need[2] else None
+    dwqkv = linear_wgrad(dqkv, h, wqkv_shape, params[0]) if need[1] else None
+    dbqkv = bias_grad(dqkv, params[1]) if need[2] else None
     dh = linear_dgrad(dqkv, wqkv16) if need[0] else None
     return dh, dwqkv, dbqkv, dwo, dbo
 
@@ -172,15 +222,15 @@ def _mlp_fwd(h, w116, b1, w216, b2, residual):
     return out, gp, a
 
 
-def _mlp_bwd(dout, h, z, a, w116, w216, w1_shape, w2_shape, need):
-    """need = (dh, dW1, db1, dW2, db2)"""
-    dw2 = linear_wgrad(dout, a, w2_shape) if need[3] else None
-    db2 = bias_grad(dout) if need[4] else None
+def _mlp_bwd(dout, h, z, a, w116, w216, w1_shape, w2_shape, need, params=(None, None, None, None)):
+    """need = (dh, dW1, db1, dW2, db2); params = (W1, b1, W2, b2) Parameters for in-place gradient accumulation"""
+    dw2 = linear_wgrad(dout, a, w2_shape, params[2]) if need[3] else None
+    db2 = bias_grad(dout, params[3]) if need[4] else None
     if not (need[0] or need[1] or need[2]):
         return None, None, None, dw2, db2
     dz = linear_dgrad(dout, w216, mul=z)  # z holds gelu'(pre-activation), saved by the forward epilogue
-    dw1 = linear_wgrad(dz, h, w1_shape) if need[1] else None
-    db1 = bias_grad(dz) if need[2] else None
+    dw1 = linear_wgrad(dz, h, w1_shape, params[0]) if need[1] else None
+    db1 = bias_grad(dz, params[1]) if need[2] else None
     dh = linear_dgrad(dz, w116) if need[0] else None
     return dh, dw1, db1, dw2, db2
 
@@ -198,15 +248,21 @@ class LayerNormFn(Function):
         ctx.save_for_backward(x2, w, mean, rstd)
         ctx.in_dtype = x.dtype
         ctx.shape = shape
+        ctx.params = (weight, bias)
         return _like_input(y, x.dtype).view(shape)
 
     @staticmethod
     def backward(ctx, dy):
         x2, w, mean, rstd = ctx.saved_tensors
         need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        dg = torch.zeros_like(w) if need_w else None
-        db = torch.zeros_like(w) if need_b else None
+        dg, db, ig, ib = _ln_grad_buffers(ctx.params[0], ctx.params[1], w, need_w, need_b)
         dx = L.layernorm_bwd(_grad2d(dy), x2, w, mean, rstd, dgamma=dg, dbeta=db)
+        if ig:
+            grad_done(ctx.params[0])
+            dg = None
+        if ib:
+            grad_done(ctx.params[1])
+            db = None
         dx = dx.view(ctx.shape)
         if ctx.in_dtype != torch.bfloat16:
             dx = dx.to(ctx.in_dtype)
@@ -322,6 +378,7 @@ class BlockFn(Function):
         out, z, a = _mlp_fwd(h2, w116, _f32c(b1), w216, _f32c(b2), xa)
         ctx.save_for_backward(x2, h1, mean1, rstd1, qkv, o, lse, xa, h2, mean2, rstd2, z, a, g1c, g2c, wqkv16, wo16, w116, w216)
         ctx.meta = (batch, seq, heads, wqkv.shape, wo.shape, w1.shape, w2.shape, x.dtype)
+        ctx.params = (g1, be1, wqkv, bqkv, wo, bo, g2, be2, w1, b1, w2, b2)  # for in-place gradient accumulation
         return _like_input(out, x.dtype).view(batch, seq, e)
 
     @staticmethod
@@ -334,24 +391,35 @@ class BlockFn(Function):
         need_upstream = n[0] or any(n[1:7])
         need_dh2 = need_upstream or n[7] or n[8]
         # ---- MLP branch ----
-        dh2, dw1, db1, dw2, db2 = _mlp_bwd(d_out, h2, z, a, w116, w216, w1_shape, w2_shape, (need_dh2, n[9], n[10], n[11], n[12]))
+        P = ctx.params
+        dh2, dw1, db1, dw2, db2 = _mlp_bwd(d_out, h2, z, a, w116, w216, w1_shape, w2_shape, (need_dh2, n[9], n[10], n[11], n[12]), P[8:12])
         dg2 = db_2 = None
         d_xa = d_out
         if dh2 is not None and (need_upstream or n[7] or n[8]):
-            dg2 = torch.zeros_like(g2c) if n[7] else None
-            db_2 = torch.zeros_like(g2c) if n[8] else None
+            dg2, db_2, ig, ib = _ln_grad_buffers(P[6], P[7], g2c, n[7], n[8])
             d_xa = L.layernorm_bwd(dh2, xa, g2c, mean2, rstd2, dres=d_out, dgamma=dg2, dbeta=db_2)  # = dout + LN2'(dh2)
+            if ig:
+                grad_done(P[6])
+                dg2 = None
+            if ib:
+                grad_done(P[7])
+                db_2 = None
         if not need_upstream:
             return (None, None, None, None, None, None, None, dg2, db_2, dw1, db1, dw2, db2, None, None)
         # ---- attention branch ----
         need_dh1 = n[0] or n[1] or n[2]
-        dh1, dwqkv, dbqkv, dwo, dbo = _attn_bwd(d_xa, h1, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, (need_dh1, n[3], n[4], n[5], n[6]), batch, seq, heads)
+        dh1, dwqkv, dbqkv, dwo, dbo = _attn_bwd(d_xa, h1, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, (need_dh1, n[3], n[4], n[5], n[6]), batch, seq, heads, P[2:6])
         dg1 = db_1 = None
         dx = None
         if dh1 is not None:
-            dg1 = torch.zeros_like(g1c) if n[1] else None
-            db_1 = torch.zeros_like(g1c) if n[2] else None
+            dg1, db_1, ig, ib = _ln_grad_buffers(P[0], P[1], g1c, n[1], n[2])
             dx = L.layernorm_bwd(dh1, x2, g1c, mean1, rstd1, dres=d_xa, dgamma=dg1, dbeta=db_1)
+            if ig:
+                grad_done(P[0])
+                dg1 = None
+            if ib:
+                grad_done(P[1])
+                db_1 = None
         if n[0]:
             dx = (dx if dx is not None else d_xa).view(batch, seq, -1)
             if in_dtype != torch.bfloat16:
@@ -376,6 +444,7 @@ class EmbedFn(Function):
         tokens, _ = L.assemble_tokens(po, None, clsf, posf, n, np_, e)
         ctx.save_for_backward(patches)
         ctx.meta = (n, np_, e, conv_w.shape, cls.shape, pos.shape)
+        ctx.params = (conv_w, conv_b, cls, pos)
         return tokens.view(n, np_ + 1, e)
 
     @staticmethod
@@ -384,9 +453,16 @@ class EmbedFn(Function):
         n, np_, e, w_shape, cls_shape, pos_shape = ctx.meta
         need = ctx.needs_input_grad
         d2 = _grad2d(dtok)
-        dcls = torch.zeros(e, device=d2.device, dtype=torch.float32) if need[3] else None
-        dpos = torch.zeros(np_ + 1, e, device=d2.device, dtype=torch.float32) if need[4] else None
+        conv_w, conv_b, cls_p, pos_p = ctx.params
+        tcls, tpos = (grad_target(cls_p) if need[3] else None), (grad_target(pos_p) if need[4] else None)
+        dcls = tcls.view(e) if tcls is not None else (torch.zeros(e, device=d2.device, dtype=torch.float32) if need[3] else None)
+        dpos = tpos.view(np_ + 1, e) if tpos is not None else (torch.zeros(np_ + 1, e, device=d2.device, dtype=torch.float32) if need[4] else None)
         dpatch = L.assemble_tokens_bwd(d2, dcls, dpos, n, np_, e)
-        dw = linear_wgrad(dpatch, patches, w_shape) if need[1] else None
-        db = bias_grad(dpatch) if need[2] else None
-        return (None, dw, db, dcls.view(cls_shape) if dcls is not None else None, dpos.view(pos_shape) if dpos is not None else None, None)
+        if tcls is not None:
+            grad_done(cls_p)
+        if tpos is not None:
+            grad_done(pos_p)
+        dw = linear_wgrad(dpatch, patches, w_shape, conv_w) if need[1] else None
+        db = bias_grad(dpatch, conv_b) if need[2] else None
+        return (None, dw, db, dcls.view(cls_shape) if (dcls is not None and tcls is None) else None,
+                dpos.view(pos_shape) if (dpos is not None and tpos is None) else None, None)
