@@ -165,15 +165,16 @@ int vb_layernorm_pair_sqdiff(const float* a, const float* b, float* u, int32_t n
  * src/vitef/optim.py:76-82 torch.optim.SGD(momentum)). The trainable parameters keep their own fp32 allocations (the
  * reference's state_dict); their gradients and momentum buffers live back to back in two flat f32 arenas.
  * ------------------------------------------------------------------------------------------------ */
-/* out[0] += sum_i x[i]^2 (x 16-byte aligned; caller zeroes out) */
-int vb_sumsq_f32(const float* x, int64_t n, float* out, vb_stream_t stream);
+/* partials[b] = sum of x[i]^2 over block b's grid-stride share, b < n_partials (x 16-byte aligned). No atomics: the
+ * total is bit-reproducible, so data-parallel replicas derive identical clip coefficients. */
+int vb_sumsq_partials_f32(const float* x, int64_t n, float* partials, int32_t n_partials, vb_stream_t stream);
 /* chunk_table: DEVICE array of n_chunks records {float* param; int64 arena_offset; int32 count; int32 pad} (24 bytes),
- * chunk starts 16-byte aligned. With norm = sqrt(*sumsq) and coef = min(1, max_norm / (norm + 1e-6)):
+ * chunk starts 16-byte aligned. With norm = sqrt(sum of the partials) and coef = min(1, max_norm / (norm + 1e-6)):
  *   g = coef * grad + weight_decay * p;  v = first_step ? g : momentum * v + g (skipped if momentum == 0);  p -= lr * v.
  * *grad_norm_out (optional) = norm, the value train.py logs as grad_norm. */
 int vb_sgd_momentum_clip_step(const void* chunk_table, int32_t n_chunks, const float* grad_arena, float* momentum_arena,
-                              const float* sumsq, float* grad_norm_out, float max_norm, float lr, float momentum,
-                              float weight_decay, int32_t first_step, vb_stream_t stream);
+                              const float* sumsq_partials, int32_t n_partials, float* grad_norm_out, float max_norm, float lr,
+                              float momentum, float weight_decay, int32_t first_step, vb_stream_t stream);
 
 #ifdef __cplusplus
 }

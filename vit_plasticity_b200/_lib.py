@@ -100,10 +100,10 @@ SIGNATURES = {
     "vb_add_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vb_rowsumsq_diff_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "vb_layernorm_pair_sqdiff": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
-    "vb_sumsq_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "vb_sumsq_partials_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
     "vb_sgd_momentum_clip_step": (
         c_int32,
-        [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int32, c_void_p],
+        [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_float, c_float, c_float, c_float, c_int32, c_void_p],
     ),
 }
 
@@ -363,17 +363,17 @@ def layernorm_pair_sqdiff(a, b, u, n_samples, rows_per_sample, cols, eps):
 # --------------------------------------------------------------------------------------------------
 # Fused optimizer step
 # --------------------------------------------------------------------------------------------------
-def sumsq_f32(x: torch.Tensor, out: torch.Tensor) -> None:
-    """out[0] += sum(x^2)"""
+def sumsq_partials_f32(x: torch.Tensor, partials: torch.Tensor) -> None:
+    """partials[b] = block b's share of sum(x^2); deterministic (no atomics)"""
     _req(x, torch.float32, "x")
-    _req(out, torch.float32, "out")
-    assert x.is_contiguous()
-    _check(lib().vb_sumsq_f32(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vb_sumsq_f32")
+    _req(partials, torch.float32, "partials")
+    assert x.is_contiguous() and partials.is_contiguous()
+    _check(lib().vb_sumsq_partials_f32(x.data_ptr(), x.numel(), partials.data_ptr(), partials.numel(), _stream()), "vb_sumsq_partials_f32")
 
 
-def sgd_momentum_clip_step(table, n_chunks, grad_arena, momentum_arena, sumsq, norm_out, max_norm, lr, momentum, weight_decay, first_step):
+def sgd_momentum_clip_step(table, n_chunks, grad_arena, momentum_arena, partials, norm_out, max_norm, lr, momentum, weight_decay, first_step):
     _check(
-        lib().vb_sgd_momentum_clip_step(table.data_ptr(), n_chunks, grad_arena.data_ptr(), _ptr(momentum_arena), sumsq.data_ptr(), _ptr(norm_out),
-                                        float(max_norm), float(lr), float(momentum), float(weight_decay), int(first_step), _stream()),
+        lib().vb_sgd_momentum_clip_step(table.data_ptr(), n_chunks, grad_arena.data_ptr(), _ptr(momentum_arena), partials.data_ptr(), partials.numel(),
+                                        _ptr(norm_out), float(max_norm), float(lr), float(momentum), float(weight_decay), int(first_step), _stream()),
         "vb_sgd_momentum_clip_step",
     )

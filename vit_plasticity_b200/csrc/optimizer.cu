@@ -12,7 +12,20 @@ namespace vb {
 
 constexpr int OPT_THREADS = 256;
 
-// out[0] += sum_i x[i]^2
+// Fixed-order tree sum of a block's values (same result on every run and every rank: data-parallel replicas must compute
+// bit-identical clip coefficients from their bit-identical all-reduced gradients).
+__device__ __forceinline__ float block_sum_deterministic(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32) t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+    __syncthreads();
+    return red[0];
+}
+
+// partials[blockIdx.x] = sum over this block's grid-stride share of x[i]^2 (no atomics: deterministic)
 __global__ void __launch_bounds__(OPT_THREADS) sumsq_f32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
     __shared__ float red[OPT_THREADS / 32];
     const int64_t n4 = n >> 2;
@@ -33,14 +46,8 @@ __global__ void __launch_bounds__(OPT_THREADS) sumsq_f32_kernel(const float* __r
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (int64_t j = n4 << 2; j < n; ++j) a0 += x[j] * x[j];
-    float acc = warp_sum((a0 + a1) + (a2 + a3));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float t = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.f;
-        t = warp_sum(t);
-        if (threadIdx.x == 0) atomicAdd(out, t);
-    }
+    const float t = block_sum_deterministic((a0 + a1) + (a2 + a3), red);
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
 }
 
 struct OptChunk {
@@ -54,10 +61,13 @@ struct OptChunk {
 // v <- momentum v + g  (first step: v = g);  p <- p - lr (v or g)
 __global__ void __launch_bounds__(OPT_THREADS)
 sgd_momentum_clip_kernel(const OptChunk* __restrict__ table, const float* __restrict__ grad, float* __restrict__ mom,
-                         const float* __restrict__ sumsq, float* __restrict__ norm_out, float max_norm, float lr, float momentum,
-                         float weight_decay, int first_step) {
+                         const float* __restrict__ sumsq_partials, int n_partials, float* __restrict__ norm_out, float max_norm,
+                         float lr, float momentum, float weight_decay, int first_step) {
+    __shared__ float red[OPT_THREADS / 32];
     const OptChunk c = table[blockIdx.x];
-    const float norm = sqrtf(__ldg(sumsq));
+    float part = 0.f;
+    for (int i = threadIdx.x; i < n_partials; i += OPT_THREADS) part += __ldg(sumsq_partials + i);  // fixed order per thread
+    const float norm = sqrtf(block_sum_deterministic(part, red));
     if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out != nullptr) *norm_out = norm;
     const float coef = fminf(1.f, max_norm / (norm + 1e-6f));
     const float* g = grad + c.arena_off;
@@ -103,30 +113,25 @@ sgd_momentum_clip_kernel(const OptChunk* __restrict__ table, const float* __rest
 
 }  // namespace vb
 
-extern "C" int vb_sumsq_f32(const float* x, int64_t n, float* out, vb_stream_t stream_) {
+extern "C" int vb_sumsq_partials_f32(const float* x, int64_t n, float* partials, int32_t n_partials, vb_stream_t stream_) {
     using namespace vb;
-    VB_CHECK_ARG(x && out && n >= 0, "vb_sumsq_f32: bad args");
-    VB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "vb_sumsq_f32: x must be 16-byte aligned");
-    if (n == 0) return VB_OK;
-    int64_t blocks = (n / 4 + OPT_THREADS * 4 - 1) / (OPT_THREADS * 4);
-    const int64_t cap = (int64_t)num_sms() * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    sumsq_f32_kernel<<<(int)blocks, OPT_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(x, n, out);
+    VB_CHECK_ARG(x && partials && n >= 0 && n_partials > 0, "vb_sumsq_partials_f32: bad args");
+    VB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "vb_sumsq_partials_f32: x must be 16-byte aligned");
+    sumsq_f32_kernel<<<n_partials, OPT_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(x, n, partials);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
 
 extern "C" int vb_sgd_momentum_clip_step(const void* chunk_table, int32_t n_chunks, const float* grad_arena, float* momentum_arena,
-                                         const float* sumsq, float* grad_norm_out, float max_norm, float lr, float momentum,
-                                         float weight_decay, int32_t first_step, vb_stream_t stream_) {
+                                         const float* sumsq_partials, int32_t n_partials, float* grad_norm_out, float max_norm,
+                                         float lr, float momentum, float weight_decay, int32_t first_step, vb_stream_t stream_) {
     using namespace vb;
-    VB_CHECK_ARG(chunk_table && grad_arena && sumsq && n_chunks > 0, "vb_sgd_momentum_clip_step: bad args");
+    VB_CHECK_ARG(chunk_table && grad_arena && sumsq_partials && n_chunks > 0 && n_partials > 0, "vb_sgd_momentum_clip_step: bad args");
     VB_CHECK_ARG(momentum == 0.f || momentum_arena != nullptr, "vb_sgd_momentum_clip_step: momentum needs a momentum arena");
     VB_CHECK_ARG(sizeof(OptChunk) == 24, "vb_sgd_momentum_clip_step: chunk layout");
     sgd_momentum_clip_kernel<<<n_chunks, OPT_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(
-        static_cast<const OptChunk*>(chunk_table), grad_arena, momentum_arena, sumsq, grad_norm_out, max_norm, lr, momentum,
-        weight_decay, first_step);
+        static_cast<const OptChunk*>(chunk_table), grad_arena, momentum_arena, sumsq_partials, n_partials, grad_norm_out, max_norm, lr,
+        momentum, weight_decay, first_step);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }

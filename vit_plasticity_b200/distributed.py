@@ -102,6 +102,7 @@ class DataParallel(nn.Module):
         self.buckets.append(self.arena[b_start:off])
         self._expected.append(n_in_bucket)
         self._ready = [0] * len(self.buckets)
+        self._seen: set = set()
         self._handles: list = []
         self._launched = [False] * len(self.buckets)
         self.require_grad_sync = True
@@ -135,6 +136,11 @@ class DataParallel(nn.Module):
             p.grad = slot  # the optimizer / clip read (and zero_grad drops) the bucket view; no copy-out later
         if not self.require_grad_sync:
             return
+        # Idempotent per step: a gradient accumulated in place is reported by ops.grad_done while its kernel is being
+        # enqueued, and autograd still runs the post-accumulate hook afterwards (with an undefined incoming gradient).
+        if p in self._seen:
+            return
+        self._seen.add(p)
         self._ready[b] += 1
         if self._ready[b] == self._expected[b] and not self._launched[b]:
             self._launch(b)
@@ -162,6 +168,7 @@ class DataParallel(nn.Module):
             for flat in self.buckets:
                 flat.div_(self.world)
         self._handles.clear()
+        self._seen.clear()
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
 

@@ -132,7 +132,7 @@ class FusedSGD(torch.optim.Optimizer):
         self.table = torch.tensor(rows, dtype=torch.int64).to(dev)  # {ptr, arena offset, count | pad} = 24 bytes per chunk
         self.n_chunks = len(rows)
         self._ptrs = [p.data_ptr() for p in self.trainable]
-        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.partials = torch.zeros(1024, device=dev, dtype=torch.float32)  # per-block sums of squares (fixed-order reduction)
         self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self._steps = 0
         self.zero_grad()
@@ -165,9 +165,8 @@ class FusedSGD(torch.optim.Optimizer):
                 self._slot(p).add_(g)
                 p.grad = self._slot(p)
         group = self.param_groups[0]
-        self.sumsq.zero_()
-        L.sumsq_f32(self.arena, self.sumsq)
-        L.sgd_momentum_clip_step(self.table, self.n_chunks, self.arena, self.momentum_arena, self.sumsq, self.grad_norm,
+        L.sumsq_partials_f32(self.arena, self.partials)
+        L.sgd_momentum_clip_step(self.table, self.n_chunks, self.arena, self.momentum_arena, self.partials, self.grad_norm,
                                  float("inf") if max_norm is None else max_norm, group["lr"], group["momentum"], group["weight_decay"],
                                  self._steps == 0)
         self._steps += 1
