@@ -290,7 +290,28 @@ def main():
             est.squared_distances(dx1, dx2)
         reps = 5
         ms_p = timed(lambda i: est.squared_distances(dx1, dx2), reps)
-        ms_pe = timed(lambda i: est.pair_distances(hx1.to(dev, non_blocking=True), hx2.to(dev, non_blocking=True)), reps)
+        # end to end: the pair images start in pinned host memory; the next call's H2D copy runs on the side stream
+        # while the current call computes; the distance table is read back to the host every call
+        pstaged = {}
+
+        def p_prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                pstaged[i] = (hx1.to(dev, non_blocking=True), hx2.to(dev, non_blocking=True), torch.cuda.Event())
+                pstaged[i][2].record(copy_stream)
+
+        def p_step(i, last):
+            if i not in pstaged:
+                p_prefetch(i)
+            a, b, ev = pstaged.pop(i)
+            torch.cuda.current_stream().wait_event(ev)
+            a.record_stream(torch.cuda.current_stream())
+            b.record_stream(torch.cuda.current_stream())
+            if not last:
+                p_prefetch(i + 1)
+            return est.pair_distances(a, b)  # numpy on the host: D2H of the (1 + 5 n_layers) x P table
+
+        p_step(0, True)
+        ms_pe = timed(lambda i: p_step(i, i == reps - 1), reps)
         pps = world * P * reps / (ms_p / 1e3)
         plast = {"metric": f"ViT-{args.model[0].upper()}/16 plasticity pairs/s", "value": round(pps, 1), "unit": "pairs/s", "pairs_per_call": P,
                  "e2e": {"value": round(world * P * reps / (ms_pe / 1e3), 1), "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * 3 * 224 * 224 * 4 * world,

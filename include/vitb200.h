@@ -82,6 +82,9 @@ typedef struct vb_gemm_args {
     int32_t cols_per_group; /* multiple of 128 */
     int32_t n_groups;
     int32_t split_k;    /* >= 1; > 1 only with VB_EPI_F32_ADD */
+    float* out_colsum;  /* f32 [N] or NULL (single-output bf16 epilogues): out_colsum[n] += sum_m out[m,n], reduced from the
+                           epilogue registers. With out = dz (fc2 dgrad x gelu') this is fc1's bias gradient, without the
+                           extra pass over dz. Caller zeroes (or accumulates). */
 } vb_gemm_args;
 
 int vb_gemm_bf16(const vb_gemm_args* args, vb_stream_t stream);

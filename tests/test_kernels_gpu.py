@@ -145,6 +145,13 @@ def test_gemm_dgrad_mn_major_b_with_dgelu():
     L.gemm(dy, w, m=tokens, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out)
     torch.cuda.synchronize()
     _report("dgrad_mulaux", out, ref * z.float(), atol=3e-2, rtol=1e-2)
+    # fused column sums of the bf16 output (= fc1's bias gradient when out = dz)
+    cs = torch.zeros(k_in, device=DEV, dtype=torch.float32)
+    out2 = torch.empty_like(out)
+    L.gemm(dy, w, m=tokens, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out2, out_colsum=cs)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+    _report("dgrad_mulaux_colsum", cs, out.float().sum(0), atol=2e-3, rtol=1e-4)
 
 
 @pytest.mark.parametrize("tokens,n_out,k_in,split_k", [(256, 128, 256, 1), (1000, 768, 768, 3), (197 * 8, 2304, 768, 4), (333, 136, 200, 2)])

@@ -13,7 +13,7 @@ name = sys.argv[2] if len(sys.argv) > 2 else "base"
 dev = "cuda"
 model = build_model({"implementation": "vit", "model_name": name, "pretrained": False, "in21k": True, "finetuning": True, "n_classes": 10}, device=dev)
 model.train()
-opt = build_optimizer(model, "sgd", lr=1e-2, momentum=0.9)
+opt = build_optimizer(model, "sgd", lr=1e-2, momentum=0.9, fused=True)
 x = torch.randn(B, 3, 224, 224, device=dev)
 y = torch.randint(0, 10, (B,), device=dev)
 

@@ -75,6 +75,12 @@ for name, n_out, k_in, epi in [("dgrad fc2 (+dgelu)", E, FF, L.EPI_BF16_DGELU), 
     out = torch.empty(M, k_in, device=dev, dtype=torch.bfloat16)
     ms = timeit(lambda: L.gemm(dy, w, m=M, n=k_in, k=n_out, b_layout=1, epilogue=epi, aux=z, out=out))
     report(name, ms, flops=2.0 * M * n_out * k_in)
+    if epi == L.EPI_BF16_DGELU:  # the training path: saved derivative, one multiply; optionally + fused column sums (fc1 bias grad)
+        ms = timeit(lambda: L.gemm(dy, w, m=M, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out))
+        report("dgrad fc2 (x saved gelu')", ms, flops=2.0 * M * n_out * k_in)
+        cs = torch.zeros(k_in, device=dev)
+        ms = timeit(lambda: L.gemm(dy, w, m=M, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out, out_colsum=cs))
+        report("dgrad fc2 (x gelu' + colsum)", ms, flops=2.0 * M * n_out * k_in)
     del dy, w, z, out
 
 for name, n_out, k_in in [("wgrad fc1", FF, E), ("wgrad fc2", E, FF), ("wgrad qkv", F3, E), ("wgrad proj", E, E)]:

@@ -12,7 +12,7 @@ from vit_plasticity_b200.finetune import build_optimizer, train_step  # noqa: E4
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 model = build_model({"implementation": "vit", "model_name": "base", "pretrained": False, "in21k": True, "finetuning": True, "n_classes": 10}, device="cuda")
 model.train()
-opt = build_optimizer(model, "sgd", lr=1e-2, momentum=0.9)
+opt = build_optimizer(model, "sgd", lr=1e-2, momentum=0.9, fused=True)
 x = torch.randn(B, 3, 224, 224, device="cuda")
 y = torch.randint(0, 10, (B,), device="cuda")
 for _ in range(3):

@@ -55,6 +55,7 @@ class GemmArgs(Structure):
         ("cols_per_group", c_int32),
         ("n_groups", c_int32),
         ("split_k", c_int32),
+        ("out_colsum", c_void_p),
     ]
 
 
@@ -182,6 +183,7 @@ def gemm(
     cols_per_group: int = 0,
     n_groups: int = 0,
     split_k: int = 1,
+    out_colsum: torch.Tensor | None = None,
 ) -> None:
     """C[m,n] = epilogue(sum_k A[m,k] B[n,k]); see ``vb_gemm_bf16`` in include/vitb200.h.
 
@@ -212,6 +214,9 @@ def gemm(
         args.sumsq = sumsq.data_ptr()
     args.rows_per_sample, args.cols_per_group, args.n_groups = rows_per_sample, cols_per_group, n_groups
     args.split_k = split_k
+    if out_colsum is not None:
+        _req(out_colsum, torch.float32, "out_colsum")
+        args.out_colsum = out_colsum.data_ptr()
     events = GEMM_EVENTS
     if events is not None:
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

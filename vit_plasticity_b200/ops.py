@@ -121,14 +121,14 @@ def linear_fwd(x, w16, bias, *, residual=None, gelu=False, gelu_grad=False):
     return out
 
 
-def linear_dgrad(dy, w16, *, dgelu_z=None, mul=None):
+def linear_dgrad(dy, w16, *, dgelu_z=None, mul=None, colsum=None):
     """dx = dy @ W (W stored [n_out, k_in], used as-is as an MN-major B operand); optional * gelu'(z) computed from a saved
-    z (``dgelu_z``) or * a saved derivative (``mul``)."""
+    z (``dgelu_z``) or * a saved derivative (``mul``). ``colsum`` (f32 [k_in]) += column sums of dx, from the epilogue."""
     m, n_out = dy.shape
     k_in = w16.shape[1]
     dx = torch.empty(m, k_in, device=dy.device, dtype=torch.bfloat16)
     if mul is not None:
-        L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=mul, out=dx)
+        L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=mul, out=dx, out_colsum=colsum)
     elif dgelu_z is not None:
         L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_DGELU, aux=dgelu_z, out=dx)
     else:
@@ -228,9 +228,14 @@ def _mlp_bwd(dout, h, z, a, w116, w216, w1_shape, w2_shape, need, params=(None, 
     db2 = bias_grad(dout, params[3]) if need[4] else None
     if not (need[0] or need[1] or need[2]):
         return None, None, None, dw2, db2
-    dz = linear_dgrad(dout, w216, mul=z)  # z holds gelu'(pre-activation), saved by the forward epilogue
+    # fc1's bias gradient = column sums of dz: reduced inside the dgrad epilogue that produces dz (no pass over dz)
+    tb1 = grad_target(params[1]) if need[2] else None
+    db1 = tb1 if tb1 is not None else (torch.zeros(w216.shape[1], device=dout.device, dtype=torch.float32) if need[2] else None)
+    dz = linear_dgrad(dout, w216, mul=z, colsum=db1)  # z holds gelu'(pre-activation), saved by the forward epilogue
+    if tb1 is not None:
+        grad_done(params[1])
+        db1 = None
     dw1 = linear_wgrad(dz, h, w1_shape, params[0]) if need[1] else None
-    db1 = bias_grad(dz, params[1]) if need[2] else None
     dh = linear_dgrad(dz, w116) if need[0] else None
     return dh, dw1, db1, dw2, db2
 
