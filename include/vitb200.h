@@ -115,6 +115,10 @@ int vb_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int3
 int64_t vb_attention_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads);
 int vb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace,
                      int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
+/* Same, and dbias[3*E] += column sums of dqkv (the qkv Linear's bias gradient; caller zeroes or accumulates), reduced
+ * from the accumulators while they are drained instead of by a second pass over dqkv. */
+int vb_attention_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias,
+                          void* workspace, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
 /* Paired attention for the plasticity estimator: runs the core on qkv_a and qkv_b (same shapes) and writes
  * delta = attn(qkv_a) - attn(qkv_b), subtracted in fp32 before the bf16 down-cast. */
 int vb_attention_pair_delta(const void* qkv_a, const void* qkv_b, int64_t ld_qkv, void* delta, int64_t ld_delta,

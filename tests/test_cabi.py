@@ -47,8 +47,18 @@ def test_ctypes_binding_matches_header(built):
     handle = _lib.lib()
     assert handle.vb_version() >= 100
     assert isinstance(handle.vb_last_error(), bytes)
-    # struct layout: 22 fields, 8-byte aligned, no torch types
-    assert ctypes.sizeof(_lib.GemmArgs) == 8 * 4 + 4 * 6 + 8 * 7 + 4 * 4 + 8  # pointers/int64s + int32s (+ tail padding)
+    # struct layout: the ctypes mirror must agree with what the C compiler makes of include/vitb200.h
+    import subprocess
+    import tempfile
+
+    src = '#include <stddef.h>\n#include <stdio.h>\n#include "vitb200.h"\nint main(void){printf("%zu %zu %zu %zu", sizeof(vb_gemm_args), offsetof(vb_gemm_args, bias), offsetof(vb_gemm_args, split_k), offsetof(vb_gemm_args, out_colsum));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        cfile, exe = Path(d) / "layout.c", Path(d) / "layout"
+        cfile.write_text(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), str(cfile), "-o", str(exe)], check=True)
+        size, off_bias, off_split, off_cs = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    assert ctypes.sizeof(_lib.GemmArgs) == size
+    assert (_lib.GemmArgs.bias.offset, _lib.GemmArgs.split_k.offset, _lib.GemmArgs.out_colsum.offset) == (off_bias, off_split, off_cs)
 
 
 def test_argument_validation_needs_no_gpu(built):

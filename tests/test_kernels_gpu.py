@@ -266,6 +266,12 @@ def test_attention_fwd_bwd(batch, seq, heads):
     dqkv = L.attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd)
     torch.cuda.synchronize()
     _report("attn_dqkv", dqkv, qf.grad, atol=3e-2, rtol=3e-2)
+    # fused qkv-bias gradient: column sums of dqkv from the same kernel (or the column-sum pass on the long-sequence path)
+    dbias = torch.zeros(3 * e, device=DEV, dtype=torch.float32)
+    dqkv2 = L.attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dbias=dbias)
+    torch.cuda.synchronize()
+    _report("attn_dqkv_with_bias", dqkv2, qf.grad, atol=3e-2, rtol=3e-2)
+    _report("attn_dbias", dbias, qf.grad.sum(0), atol=5e-2, rtol=2e-2)
 
 
 def test_attention_pair_delta():

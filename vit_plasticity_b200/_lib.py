@@ -81,6 +81,10 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
     ),
+    "vb_attention_bwd_bias": (
+        c_int32,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    ),
     "vb_attention_pair_delta": (
         c_int32,
         [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
@@ -267,9 +271,17 @@ def attention_fwd(qkv, batch, seq, heads, head_dim, *, want_lse=True):
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, batch, seq, heads, head_dim):
+def attention_bwd(qkv, out, dout, lse, batch, seq, heads, head_dim, *, dbias=None):
+    """dqkv; with ``dbias`` (f32 [3E], accumulated into) the same kernel also reduces the column sums of dqkv."""
     dqkv = torch.empty_like(qkv)
     ws = torch.empty(int(lib().vb_attention_bwd_workspace_bytes(batch, seq, heads)), device=qkv.device, dtype=torch.uint8)
+    if dbias is not None:
+        _req(dbias, torch.float32, "dbias")
+        _check(
+            lib().vb_attention_bwd_bias(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), dbias.data_ptr(), ws.data_ptr(), batch, seq, heads, head_dim, _stream()),
+            "vb_attention_bwd_bias",
+        )
+        return dqkv
     _check(
         lib().vb_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), batch, seq, heads, head_dim, _stream()),
         "vb_attention_bwd",

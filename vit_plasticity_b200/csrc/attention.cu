@@ -442,7 +442,8 @@ int launch_attention_bwd_tc(const bf16* qkv, const bf16* out, const bf16* dout, 
 int launch_attention_fwd_tc2(const bf16* qkv, bf16* out, float* lse, int batch, int L, int H, cudaStream_t stream);
 int launch_attention_fwd_tc3(const bf16* qkv, bf16* out, float* lse, int batch, int L, int H, cudaStream_t stream);
 int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
-                             int batch, int L, int H, cudaStream_t stream);
+                             float* dbias, int batch, int L, int H, cudaStream_t stream);
+int launch_colsum_bf16(const bf16* x, int64_t ldx, float* out, int rows, int cols, cudaStream_t stream);
 int launch_attention_pair_tc3(const bf16* qkv_a, const bf16* qkv_b, int64_t ld, bf16* delta, int layers, int batch, int L, int H,
                               cudaStream_t stream);
 int launch_attention_bwd_tc2(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
@@ -521,19 +522,44 @@ extern "C" int64_t vb_attention_bwd_workspace_bytes(int32_t batch, int32_t seq, 
     return (int64_t)batch * heads * seq * 4;
 }
 
+static int attention_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace,
+                                  int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, float* dbias, bool* dbias_done,
+                                  cudaStream_t stream);
+
 extern "C" int vb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                 void* workspace, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim,
                                 vb_stream_t stream_) {
+    bool done = false;
+    return attention_bwd_dispatch(qkv, out, dout, lse, dqkv, workspace, batch, seq, heads, head_dim, nullptr, &done,
+                                  static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vb_attention_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                     float* dbias, void* workspace, int32_t batch, int32_t seq, int32_t heads,
+                                     int32_t head_dim, vb_stream_t stream_) {
     using namespace vb;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(dbias != nullptr, "vb_attention_bwd_bias: null dbias");
+    bool done = false;
+    int rc = attention_bwd_dispatch(qkv, out, dout, lse, dqkv, workspace, batch, seq, heads, head_dim, dbias, &done, stream);
+    if (rc != VB_OK || done) return rc;
+    // kernels without the fused reduction (legacy / long-sequence paths): one column-sum pass over dqkv
+    return launch_colsum_bf16(static_cast<const bf16*>(dqkv), 3LL * heads * head_dim, dbias, batch * seq, 3 * heads * head_dim, stream);
+}
+
+static int attention_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace,
+                                  int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, float* dbias, bool* dbias_done,
+                                  cudaStream_t stream) {
+    using namespace vb;
     VB_CHECK_ARG(qkv && out && dout && lse && dqkv, "vb_attention_bwd: null pointer");
     VB_CHECK_ARG(head_dim == HD, "vb_attention_bwd: head_dim must be 64 (got %d)", head_dim);
     VB_CHECK_ARG(batch > 0 && heads > 0 && seq > 0 && seq <= 272, "vb_attention_bwd: seq=%d must be in [1, 272]", seq);
     if (seq <= 208 && attn_impl() == 3) {
         VB_CHECK_ARG(workspace != nullptr, "vb_attention_bwd: workspace of vb_attention_bwd_workspace_bytes() bytes required");
+        *dbias_done = true;
         return launch_attention_bwd_tc3(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
                                         static_cast<const bf16*>(dout), lse, static_cast<float*>(workspace),
-                                        static_cast<bf16*>(dqkv), batch, seq, heads, stream);
+                                        static_cast<bf16*>(dqkv), dbias, batch, seq, heads, stream);
     }
     if (seq <= 208 && attn_impl() == 2) {
         VB_CHECK_ARG(workspace != nullptr, "vb_attention_bwd: workspace of vb_attention_bwd_workspace_bytes() bytes required");

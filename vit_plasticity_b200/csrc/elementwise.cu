@@ -332,6 +332,12 @@ extern "C" int vb_assemble_tokens_bwd(const void* dtokens, void* dpatch_out, flo
     return VB_OK;
 }
 
+namespace vb {
+int launch_colsum_bf16(const bf16* x, int64_t ldx, float* out, int rows, int cols, cudaStream_t stream) {
+    return vb_colsum_bf16(x, ldx, out, rows, cols, static_cast<vb_stream_t>(stream));
+}
+}  // namespace vb
+
 extern "C" int vb_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t rows, int32_t cols, vb_stream_t stream_) {
     using namespace vb;
     VB_CHECK_ARG(x && out, "vb_colsum_bf16: null pointer");

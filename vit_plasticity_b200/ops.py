@@ -209,9 +209,14 @@ def _attn_bwd(dout, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need, ba
     if not (need[0] or need[1] or need[2]):
         return None, None, None, dwo, dbo
     do = linear_dgrad(dout, wo16)
-    dqkv = L.attention_bwd(qkv, o, do, lse, batch, seq, heads, e // heads)
+    # the qkv bias gradient = column sums of dqkv: reduced inside the attention backward kernel while it drains dQ/dK/dV
+    tbq = grad_target(params[1]) if need[2] else None
+    dbqkv = tbq if tbq is not None else (torch.zeros(qkv.shape[1], device=qkv.device, dtype=torch.float32) if need[2] else None)
+    dqkv = L.attention_bwd(qkv, o, do, lse, batch, seq, heads, e // heads, dbias=dbqkv)
+    if tbq is not None:
+        grad_done(params[1])
+        dbqkv = None
     dwqkv = linear_wgrad(dqkv, h, wqkv_shape, params[0]) if need[1] else None
-    dbqkv = bias_grad(dqkv, params[1]) if need[2] else None
     dh = linear_dgrad(dqkv, wqkv16) if need[0] else None
     return dh, dwqkv, dbqkv, dwo, dbo
 
