@@ -437,26 +437,21 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
 }
 
 // tcgen05 implementations, used for seq <= 208 (ViT-B/L at 224x224)
-int launch_attention_bwd_tc(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int batch, int L,
-                            int H, cudaStream_t stream);  // attention_tc.cu: single kernel, P/dS through smem
-int launch_attention_fwd_tc2(const bf16* qkv, bf16* out, float* lse, int batch, int L, int H, cudaStream_t stream);
 int launch_attention_fwd_tc3(const bf16* qkv, bf16* out, float* lse, int batch, int L, int H, cudaStream_t stream);
 int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
                              float* dbias, int batch, int L, int H, cudaStream_t stream);
 int launch_colsum_bf16(const bf16* x, int64_t ldx, float* out, int rows, int cols, cudaStream_t stream);
 int launch_attention_pair_tc3(const bf16* qkv_a, const bf16* qkv_b, int64_t ld, bf16* delta, int layers, int batch, int L, int H,
                               cudaStream_t stream);
-int launch_attention_bwd_tc2(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
-                             int batch, int L, int H, cudaStream_t stream);  // attention_tc2.cu: 2 CTAs/SM, P/dS in TMEM
 
-// Development aid only (never set by the package): VITB200_ATTN=mma forces the legacy mma.sync kernels,
-// VITB200_ATTN=tc1 the single-kernel tcgen05 backward, VITB200_ATTN=tc2 the one-CTA-per-tile TMEM-operand kernels of
-// attention_tc2.cu; default = the persistent pipelined kernels of attention_tc3.cu.
+// Development aid only (never set by the package): VITB200_ATTN=mma forces the mma.sync kernels of this file (the
+// production path for sequences of 209..272 tokens) for every length; default = the persistent tcgen05 kernels of
+// attention_tc3.cu for seq <= 208.
 static int attn_impl() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("VITB200_ATTN");
-        v = (e == nullptr) ? 3 : (e[0] == 'm' ? 0 : (e[0] == 't' && e[2] == '1' ? 1 : (e[0] == 't' && e[2] == '2' ? 2 : 3)));
+        v = (e != nullptr && e[0] == 'm') ? 0 : 3;
     }
     return v;
 }
@@ -473,8 +468,6 @@ extern "C" int vb_attention_fwd(const void* qkv, void* out, float* lse, int32_t 
     const int64_t E = (int64_t)heads * HD;
     if (seq <= 208 && attn_impl() == 3)
         return launch_attention_fwd_tc3(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, batch, seq, heads, stream);
-    if (seq <= 208 && attn_impl() == 2)
-        return launch_attention_fwd_tc2(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, batch, seq, heads, stream);
     if (seq <= 208)
         return launch_fwd<13, false>(static_cast<const bf16*>(qkv), nullptr, 3 * E, static_cast<bf16*>(out), E, lse, batch,
                                      seq, heads, stream);
@@ -561,15 +554,6 @@ static int attention_bwd_dispatch(const void* qkv, const void* out, const void* 
                                         static_cast<const bf16*>(dout), lse, static_cast<float*>(workspace),
                                         static_cast<bf16*>(dqkv), dbias, batch, seq, heads, stream);
     }
-    if (seq <= 208 && attn_impl() == 2) {
-        VB_CHECK_ARG(workspace != nullptr, "vb_attention_bwd: workspace of vb_attention_bwd_workspace_bytes() bytes required");
-        return launch_attention_bwd_tc2(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
-                                        static_cast<const bf16*>(dout), lse, static_cast<float*>(workspace),
-                                        static_cast<bf16*>(dqkv), batch, seq, heads, stream);
-    }
-    if (seq <= 208 && attn_impl() == 1)
-        return launch_attention_bwd_tc(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
-                                       static_cast<const bf16*>(dout), lse, static_cast<bf16*>(dqkv), batch, seq, heads, stream);
     if (seq <= 208)
         return launch_bwd<13>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(dout),
                               lse, static_cast<bf16*>(dqkv), batch, seq, heads, stream);
