@@ -154,6 +154,12 @@ int vb_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t rows, int32_t
 /* y = a + b (bf16), n elements */
 int vb_add_bf16(const void* a, const void* b, void* y, int64_t n, vb_stream_t stream);
 
+/* Probe pooling (apps/vit/linear_probing.py:92-103,109-112): pooled[n,:] = x[n,0,:] (cls_pooling) or the mean over the
+ * seq tokens, optionally L2-normalised per row. x: bf16 [n, seq, dim]; pooled: f32 [n, dim]. Keeps the 8 taps per block
+ * of get_probes on the device: (n, dim) rows go to the host instead of (n, seq, dim) tensors. */
+int vb_pool_tokens(const void* x, float* pooled, int32_t n, int32_t seq, int32_t dim, int32_t cls_pooling, int32_t normalize,
+                   vb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Plasticity reductions (apps/vit/analysis.py:68 `distance`; apps/plots/analysis.py:97 ratio)
  * ------------------------------------------------------------------------------------------------ */

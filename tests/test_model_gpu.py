@@ -336,6 +336,16 @@ def test_decomposition_and_probes_api_tiny():
         assert v.device.type == "cpu" and v.dtype == torch.float32
         assert rel_l2(v[:, 0, :], gold["probes"][k]["cls"]) <= 3e-2, k
         assert rel_l2(v.mean(1), gold["probes"][k]["mean"]) <= 3e-2, k
+    # on-device pooling for linear probing == pooling + row normalisation of the reference's taps
+    for cls_pooling, field in ((True, "cls"), (False, "mean")):
+        pooled = model.get_pooled_probes(x.to(DEV), cls_pooling=cls_pooling)
+        assert list(pooled) == list(gold["probes"])
+        for k, v in pooled.items():
+            ref_rows = gold["probes"][k][field].float()
+            ref_rows = ref_rows / ref_rows.norm(dim=-1, keepdim=True)
+            assert v.device.type == "cpu" and v.shape == ref_rows.shape
+            assert rel_l2(v, ref_rows) <= 3e-2, (k, field)
+            assert torch.allclose(v.norm(dim=-1), torch.ones(v.shape[0]), atol=1e-4)
     dec = model.get_decomposition(x.to(DEV))
     ref = O.decomposition(sd, x, arch)
     assert list(dec) == list(ref) and len(dec) == 1 + 5 * arch.n_layers

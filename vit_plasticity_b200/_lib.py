@@ -103,6 +103,7 @@ SIGNATURES = {
     "vb_assemble_tokens_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "vb_colsum_bf16": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p]),
     "vb_add_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vb_pool_tokens": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "vb_rowsumsq_diff_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "vb_layernorm_pair_sqdiff": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "vb_sumsq_partials_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
@@ -367,6 +368,16 @@ def add_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     y = torch.empty_like(a)
     _check(lib().vb_add_bf16(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream()), "vb_add_bf16")
     return y
+
+
+def pool_tokens(x: torch.Tensor, n: int, seq: int, cls_pooling: bool, normalize: bool = True) -> torch.Tensor:
+    """f32 [n, dim]: cls row or token mean of a bf16 [n*seq, dim] / [n, seq, dim] activation, L2-normalised per row."""
+    _req(x, torch.bfloat16, "x")
+    assert x.is_contiguous()
+    dim = x.shape[-1]
+    out = torch.empty(n, dim, device=x.device, dtype=torch.float32)
+    _check(lib().vb_pool_tokens(x.data_ptr(), out.data_ptr(), n, seq, dim, int(cls_pooling), int(normalize), _stream()), "vb_pool_tokens")
+    return out
 
 
 def rowsumsq_diff_f32(a, b, out, n_samples, rows_per_sample, cols):

@@ -249,6 +249,44 @@ rowsumsq_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, f
     }
 }
 
+// pooled[n, :] = x[n, 0, :] (cls) or mean_l x[n, l, :], optionally divided by its L2 norm. One block per sample,
+// thread t owns feature pairs t, t + 256, ...; the token loop reads 4 B per thread per token (coalesced rows).
+__global__ void __launch_bounds__(EW_THREADS)
+pool_tokens_kernel(const bf16* __restrict__ x, float* __restrict__ pooled, int seq, int dim, int cls_pooling, int normalize) {
+    __shared__ float red[EW_THREADS / 32];
+    const int n = blockIdx.x;
+    const bf16* xs = x + (size_t)n * seq * dim;
+    float* out = pooled + (size_t)n * dim;
+    const int rows = cls_pooling ? 1 : seq;
+    const float scale = 1.f / (float)rows;
+    float ss = 0.f;
+    for (int p = threadIdx.x; p < dim / 2; p += EW_THREADS) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int l = 0; l < rows; ++l) {
+            const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(xs + (size_t)l * dim) + p));
+            a0 += f.x;
+            a1 += f.y;
+        }
+        a0 *= scale;
+        a1 *= scale;
+        out[2 * p] = a0;
+        out[2 * p + 1] = a1;
+        ss += a0 * a0 + a1 * a1;
+    }
+    if (!normalize) return;
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < EW_THREADS / 32; ++w) tot += red[w];
+    const float inv = rsqrtf(tot);
+    for (int p = threadIdx.x; p < dim / 2; p += EW_THREADS) {  // each thread rescales the values it wrote itself
+        out[2 * p] *= inv;
+        out[2 * p + 1] *= inv;
+    }
+}
+
 static inline int ew_grid(int64_t work_items) {
     int64_t g = (work_items + EW_THREADS - 1) / EW_THREADS;
     const int64_t cap = (int64_t)num_sms() * 16;
@@ -350,6 +388,17 @@ extern "C" int vb_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t ro
     dim3 grid(col_blocks, (rows + rows_per_block - 1) / rows_per_block);
     colsum_bf16_kernel<<<grid, EW_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<const bf16*>(x), ldx, out,
                                                                                    rows, cols, rows_per_block);
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+extern "C" int vb_pool_tokens(const void* x, float* pooled, int32_t n, int32_t seq, int32_t dim, int32_t cls_pooling,
+                              int32_t normalize, vb_stream_t stream_) {
+    using namespace vb;
+    VB_CHECK_ARG(x && pooled, "vb_pool_tokens: null pointer");
+    VB_CHECK_ARG(n > 0 && seq > 0 && dim > 0 && dim % 2 == 0, "vb_pool_tokens: need n, seq > 0 and an even dim (n=%d seq=%d dim=%d)", n, seq, dim);
+    pool_tokens_kernel<<<n, EW_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<const bf16*>(x), pooled, seq, dim,
+                                                                               cls_pooling, normalize);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }

@@ -176,6 +176,31 @@ class TransformerBlock(nn.Module):
         return out, probes
 
 
+    @torch.inference_mode()
+    def _pooled_probes(self, x: torch.Tensor, cls_pooling: bool, normalize: bool):
+        """The 8 taps of ``_probes`` pooled on the device (cls row or token mean, L2-normalised): what
+        apps/vit/linear_probing.py:92-112 computes on the host after copying every (N, L, D) tap over PCIe."""
+        n, seq, _ = x.shape
+        pool = lambda t: L.pool_tokens(ops._as_bf16_2d(t), n, seq, cls_pooling, normalize)
+        probes = {}
+        out = self.attn_norm(x)
+        probes["attn_norm"] = pool(out)
+        out = self.attn(out)
+        probes["attn"] = pool(out)
+        out_res = L.add_bf16(ops._as_bf16_2d(x), ops._as_bf16_2d(out)).view(out.shape)
+        probes["attn_res"] = pool(out_res)
+        out = self.ffn_norm(out_res)
+        probes["ffn_norm"] = pool(out)
+        act, z = ops.linear_fwd(ops._as_bf16_2d(out), ops.shadow_bf16(self.ffn.fc1.weight), self.ffn.fc1.bias.detach(), gelu=True)
+        probes["ffn_fc1"] = pool(z)
+        probes["ffn_activation"] = pool(act)
+        out = self.ffn.fc2(act).view(out_res.shape)
+        probes["ffn_fc2"] = pool(out)
+        out = L.add_bf16(ops._as_bf16_2d(out_res), ops._as_bf16_2d(out)).view(out_res.shape)
+        probes["ffn_res"] = pool(out)
+        return out, probes
+
+
 class PatchImages(nn.Module):
     """Hybrid patching (transformer/utils.py:38-115): a Conv2d with kernel = stride = P holds the weights
     (``patching.0``, shape (E, C, P, P)); the forward is im2col + the tcgen05 GEMM."""
@@ -306,6 +331,18 @@ class Transformer(nn.Module):
             for key, val in block._decompose(out).items():
                 outputs[f"block{i}_{key}"] = val
         return outputs
+
+    @torch.inference_mode()
+    def get_pooled_probes(self, x: torch.Tensor, cls_pooling: bool = True, normalize: bool = True) -> dict:
+        """``get_probes`` followed by the pooling + normalisation of linear_probing.get_embeddings, done on the device:
+        {key: (N, D) float32 CPU tensor}. 96 x (N, D) rows cross PCIe per batch instead of 96 x (N, 197, D) tensors."""
+        probes = {}
+        out = self.embedding(x)
+        for i, block in enumerate(self.blocks):
+            out, block_probes = block._pooled_probes(out, cls_pooling, normalize)
+            for key, val in block_probes.items():
+                probes[f"block{i}_{key}"] = val
+        return {k: v.cpu() for k, v in probes.items()}
 
     @torch.inference_mode()
     def get_probes(self, x: torch.Tensor) -> dict:

@@ -49,6 +49,7 @@ class ViT(nn.Module):
         self.forward = self.model.forward
         self.get_decomposition = self.model.get_decomposition
         self.get_probes = self.model.get_probes
+        self.get_pooled_probes = self.model.get_pooled_probes  # on-device pooling for linear probing (not in the reference)
 
         if vit_config.pretrained:
             self.save_dir = vit_config.save_dir
