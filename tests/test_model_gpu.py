@@ -324,6 +324,31 @@ def test_perturbation_sweep_matches_oracle_and_is_shard_invariant():
             assert np.allclose(both, full[eps][k], rtol=1e-5, atol=0), (eps, k)
 
 
+def test_analysis_loop_writes_reference_distances_pkl(tmp_path):
+    """analysis(): the reference's loop and on-disk format (apps/vit/analysis.py:203-248) on the fused estimator."""
+    import pickle
+
+    from vit_plasticity_b200.plasticity import analysis, get_plasticity
+
+    gold = load("tiny")
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    model = build("tiny", gold, arch, sd).eval()
+    mk = lambda seed: [(O.synthetic_images(3, arch, seed + i), torch.zeros(3, dtype=torch.long)) for i in range(2)]
+    l1, l2 = mk(60), mk(70)
+    dist = analysis(model, l1, l2, n_steps=3, save_dir=tmp_path)  # 3 steps over 2-batch loaders: the loaders wrap around
+    saved = pickle.load(open(tmp_path / "distances.pkl", "rb"))
+    assert list(saved) == list(dist) and len(saved) == 1 + 5 * arch.n_layers
+    for k, v in saved.items():
+        assert isinstance(v, np.ndarray) and v.dtype == np.float32 and v.shape == (9,)
+    ref = O.pair_distances(sd, l1[1][0], l2[1][0], arch)  # second batch pair sits at positions 3..5
+    for k in ref:
+        assert np.allclose(saved[k][3:6] / saved["embedding"][3:6], ref[k] / ref["embedding"], rtol=2e-2), k
+    assert np.allclose(saved["embedding"][6:9], saved["embedding"][0:3])  # wrap-around: third step = first batch pair again
+    plast = get_plasticity(saved)
+    assert set(plast) == {"attn_norm", "attn", "ffn_norm", "ffn_fc1", "ffn_fc2"} and all(len(v) == arch.n_layers for v in plast.values())
+
+
 def test_decomposition_and_probes_api_tiny():
     gold = load("tiny")
     arch = arch_of(gold)

@@ -210,6 +210,37 @@ def perturbation_sweep(model, images, eps_list, noise_seed: int = 0, pairs_per_c
     return out
 
 
+def analysis(model, loader1, loader2, n_steps: int, save_dir=None, device=None) -> dict[str, np.ndarray]:
+    """Drop-in for the loop of apps/vit/analysis.py:188-248: batch k of ``loader1`` is paired with batch k of
+    ``loader2`` (iterables of (images, labels)), the per-sample distances of every component are accumulated with the
+    reference's ``update_dict`` semantics and, if ``save_dir`` is given, written to ``save_dir/distances.pkl`` in the
+    reference's format (a pickled {key: float32 ndarray of length n_steps * batch}), which apps/plots/analysis.py reads.
+    Loaders are re-iterated when exhausted, like ``make_iterable`` (src/vitef/utils.py)."""
+    import pickle
+    from pathlib import Path
+
+    est = PlasticityEstimator(model)
+    dev = device if device is not None else next(_inner(model).parameters()).device
+
+    def forever(loader):
+        while True:
+            yield from loader
+
+    it1, it2 = forever(loader1), forever(loader2)
+    distances: dict[str, np.ndarray] = {}
+    for _ in range(n_steps):
+        x1, _y1 = next(it1)
+        x2, _y2 = next(it2)
+        if not x1.is_cuda:
+            x1, x2 = x1.pin_memory().to(dev, non_blocking=True), x2.pin_memory().to(dev, non_blocking=True)
+        update_distances(distances, est.pair_distances(x1, x2))
+    if save_dir is not None:
+        Path(save_dir).mkdir(parents=True, exist_ok=True)
+        with open(Path(save_dir) / "distances.pkl", "wb") as f:
+            pickle.dump(distances, f)
+    return distances
+
+
 def pair_distances(model, x1, x2) -> dict[str, np.ndarray]:
     return PlasticityEstimator(model).pair_distances(x1, x2)
 
