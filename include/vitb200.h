@@ -81,13 +81,18 @@ typedef struct vb_gemm_args {
     int32_t rows_per_sample;
     int32_t cols_per_group; /* multiple of 128 */
     int32_t n_groups;
-    int32_t split_k;    /* >= 1; > 1 only with VB_EPI_F32_ADD */
+    int32_t split_k;    /* >= 1 (> 1 only with VB_EPI_F32_ADD); <= 0: chosen by the library to fill the SMs */
     float* out_colsum;  /* f32 [N] or NULL (single-output bf16 epilogues): out_colsum[n] += sum_m out[m,n], reduced from the
                            epilogue registers. With out = dz (fc2 dgrad x gelu') this is fc1's bias gradient, without the
                            extra pass over dz. Caller zeroes (or accumulates). */
 } vb_gemm_args;
 
 int vb_gemm_bf16(const vb_gemm_args* args, vb_stream_t stream);
+/* Tile mapping of vb_gemm_bf16: 1 (default; env VB_GEMM_CTA_PAIR=0 turns it off) = a CTA pair per 256 x 256 tile with
+ * tcgen05.mma.cta_group::2 (each SM stages half of the B tile), 0 = one CTA per 128 x 256 tile. Results are bit-identical
+ * per output element for split_k == 1 (same k order); the setting exists for measurement and bisection. */
+void vb_set_gemm_cta_pair(int enabled);
+int vb_get_gemm_cta_pair(void);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm (nn.LayerNorm, transformer/utils.py:293; used at architecture.py:347,349 and utils.py:396)

@@ -54,6 +54,43 @@ def _report(name, got, ref, atol, rtol):
 # ---------------------------------------------------------------------------------------------------
 # GEMM
 # ---------------------------------------------------------------------------------------------------
+@pytest.fixture(autouse=True, params=["pair", "single"])
+def _gemm_tile_mapping(request):
+    """Every GEMM test runs under both tile mappings: CTA pairs (256 x 256, tcgen05 cta_group::2; the default) and single
+    CTAs (128 x 256). Non-GEMM tests run once."""
+    if not request.node.name.startswith("test_gemm"):
+        if request.param == "single":
+            pytest.skip("tile mapping only concerns the GEMM tests")
+        yield
+        return
+    lib = _lib().lib()
+    before = lib.vb_get_gemm_cta_pair()
+    lib.vb_set_gemm_cta_pair(1 if request.param == "pair" else 0)
+    yield
+    lib.vb_set_gemm_cta_pair(before)
+
+
+def test_gemm_pair_and_single_mappings_agree_bitwise():
+    """Same k order per output element in both mappings: bf16 / fp32 outputs must be identical, not just close."""
+    L = _lib()
+    lib = L.lib()
+    m, n, k = 1000, 768, 1536
+    a = _rand(m, k, seed=1).bfloat16()
+    b = _rand(n, k, seed=2, scale=0.05).bfloat16()
+    bias = _rand(n, seed=3)
+    outs = []
+    for pair in (1, 0):
+        lib.vb_set_gemm_cta_pair(pair)
+        o16 = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+        o32 = torch.empty(m, n, device=DEV, dtype=torch.float32)
+        L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_BF16, bias=bias, out=o16)
+        L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_F32, out=o32)
+        torch.cuda.synchronize()
+        outs.append((o16, o32))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
 GEMM_SHAPES = [(128, 256, 64), (256, 256, 128), (384, 512, 256), (1000, 768, 768), (197 * 3, 2304, 768), (130, 136, 72)]
 
 
@@ -154,7 +191,7 @@ def test_gemm_dgrad_mn_major_b_with_dgelu():
     _report("dgrad_mulaux_colsum", cs, out.float().sum(0), atol=2e-3, rtol=1e-4)
 
 
-@pytest.mark.parametrize("tokens,n_out,k_in,split_k", [(256, 128, 256, 1), (1000, 768, 768, 3), (197 * 8, 2304, 768, 4), (333, 136, 200, 2)])
+@pytest.mark.parametrize("tokens,n_out,k_in,split_k", [(256, 128, 256, 1), (1000, 768, 768, 3), (197 * 8, 2304, 768, 4), (333, 136, 200, 2), (197 * 16, 768, 3072, 0)])
 def test_gemm_wgrad_mn_major_both_splitk(tokens, n_out, k_in, split_k):
     L = _lib()
     dy = _rand(tokens, n_out, seed=1).bfloat16()

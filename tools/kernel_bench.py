@@ -37,7 +37,11 @@ def rnd(*s, dt=torch.bfloat16, scale=1.0):
     return (torch.randn(*s, device=dev) * scale).to(dt)
 
 
+import os  # noqa: E402
+
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+GEMM_ONLY = os.environ.get("KB_ONLY") == "gemm"
+print(f"GEMM tile mapping: {'CTA pairs (256x256, cta_group::2)' if L.lib().vb_get_gemm_cta_pair() else 'single CTAs (128x256)'}", flush=True)
 M, E, F3, FF = B * 197, 768, 2304, 3072
 res = []
 
@@ -55,12 +59,12 @@ def report(name, ms, flops=None, bytes_=None):
 
 
 x = rnd(M, E)
-for name, n, k, epi in [("fwd qkv  bias", F3, E, L.EPI_BF16), ("fwd proj bias+resid", E, E, L.EPI_BF16_RESID), ("fwd fc1  bias+gelu", FF, E, L.EPI_BF16_GELU), ("fwd fc2  bias+resid", E, FF, L.EPI_BF16_RESID)]:
+for name, n, k, epi in [("fwd qkv  bias", F3, E, L.EPI_BF16), ("fwd proj bias+resid", E, E, L.EPI_BF16_RESID), ("fwd fc1  bias+gelu (+z)", FF, E, L.EPI_BF16_GELU), ("fwd fc1  bias+gelu+gelu' (train)", FF, E, L.EPI_BF16_GELU_GRAD), ("fwd fc1  bias only", FF, E, L.EPI_BF16), ("fwd fc2  bias+resid", E, FF, L.EPI_BF16_RESID)]:
     a = rnd(M, k)
     w = rnd(n, k, scale=0.02)
     bias = torch.randn(n, device=dev)
     out = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
-    out2 = torch.empty(M, n, device=dev, dtype=torch.bfloat16) if epi == L.EPI_BF16_GELU else None
+    out2 = torch.empty(M, n, device=dev, dtype=torch.bfloat16) if epi in (L.EPI_BF16_GELU, L.EPI_BF16_GELU_GRAD) else None
     aux = rnd(M, n) if epi == L.EPI_BF16_RESID else None
     ms = timeit(lambda: L.gemm(a, w, m=M, n=n, k=k, epilogue=epi, bias=bias, aux=aux, out=out, out2=out2))
     report(name, ms, flops=2.0 * M * n * k)
@@ -88,14 +92,16 @@ for name, n_out, k_in in [("wgrad fc1", FF, E), ("wgrad fc2", E, FF), ("wgrad qk
     xx = rnd(M, k_in)
     dw = torch.zeros(n_out, k_in, device=dev)
     tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
-    for waves in (1, 2, 4, 8):
-        sk = max(1, (148 * waves) // tiles)
+    for waves in (0, 1, 2, 4):
+        sk = max(1, (148 * waves) // tiles) if waves else 0  # 0: the library's own choice
         ms = timeit(lambda: L.gemm(dy, xx, m=n_out, n=k_in, k=M, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=sk))
         report(f"{name} split_k={sk}", ms, flops=2.0 * M * n_out * k_in)
     ref = timeit(lambda: torch.matmul(dy.T, xx))
     report("   (torch matmul dy^T x)", ref, flops=2.0 * M * n_out * k_in)
     del dy, xx, dw
 
+if GEMM_ONLY:
+    sys.exit(0)
 g, b = torch.ones(E, device=dev), torch.zeros(E, device=dev)
 ms = timeit(lambda: L.layernorm_fwd(x, g, b, 1e-12))
 report("layernorm fwd", ms, bytes_=2.0 * M * E * 2)

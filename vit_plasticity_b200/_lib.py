@@ -66,6 +66,8 @@ SIGNATURES = {
     "vb_launch_count": (c_int64, []),
     "vb_reset_launch_count": (None, []),
     "vb_gemm_bf16": (c_int32, [POINTER(GemmArgs), c_void_p]),
+    "vb_set_gemm_cta_pair": (None, [c_int32]),
+    "vb_get_gemm_cta_pair": (c_int32, []),
     "vb_layernorm_fwd": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p],

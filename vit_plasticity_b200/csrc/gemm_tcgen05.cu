@@ -20,16 +20,24 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+// G = CTAs per tile: 1 = one CTA computes 128 x 256 (cta_group::1); 2 = a CTA pair computes 256 x 256 with ONE
+// tcgen05.mma.cta_group::2 per k-step: each CTA stages its own 128 rows of A and only HALF of the B tile (128 columns),
+// so the smem operand traffic per SM per MMA drops from 12 KB to 8 KB and the ring holds 6 stages instead of 4.
+template <int G>
+struct GemmCfg {
+    static constexpr int B_STAGE_BYTES = (BN / G) * BK * 2;  // 32 KB / 16 KB
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = G == 1 ? 4 : 6;
+};
+constexpr int MAX_STAGES = 6;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_FIRST_WARP = 4;
 constexpr int STAGING_BYTES = 4096;  // per epilogue warp: 2 x (32 rows x 64 B) bf16 or 1 x (32 rows x 128 B) f32
 constexpr int GEMM_THREADS = (EPI_FIRST_WARP + EPI_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES + 256 + 1024;  // + barriers + align
+constexpr int GEMM_SMEM_BYTES = 4 * 49152 + EPI_WARPS * STAGING_BYTES + 256 + 1024;  // ring (4 x 48 KB = 6 x 32 KB) + staging + barriers + align
+static_assert(GemmCfg<1>::STAGES * GemmCfg<1>::STAGE_BYTES == 4 * 49152 && GemmCfg<2>::STAGES * GemmCfg<2>::STAGE_BYTES == 4 * 49152, "ring size");
 
 struct GemmKernelParams {
     int M, N, K;
@@ -49,21 +57,24 @@ struct WorkItem {
     int m_blk, n_blk, kb0, kb1;
 };
 
-__device__ __forceinline__ WorkItem decode_work(const GemmKernelParams& p, int w) {
+// num_m_blocks counts tiles of G x 128 rows; the returned m_blk is THIS CTA's 128-row block.
+template <int G>
+__device__ __forceinline__ WorkItem decode_work(const GemmKernelParams& p, int w, int rank) {
     // split index is the slowest so that concurrently running CTAs share the same K-slice (L2 reuse in wgrad);
     // within a split, n is fastest so CTAs running together share the A row panel.
     int tiles = p.num_m_blocks * p.num_n_blocks;
     int split = w / tiles;
     int tile = w - split * tiles;
     WorkItem it;
-    it.m_blk = tile / p.num_n_blocks;
-    it.n_blk = tile - it.m_blk * p.num_n_blocks;
+    const int mt = tile / p.num_n_blocks;
+    it.m_blk = mt * G + rank;
+    it.n_blk = tile - mt * p.num_n_blocks;
     it.kb0 = split * p.kb_per_split;
     it.kb1 = min(it.kb0 + p.kb_per_split, p.num_k_blocks);
     return it;
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int G>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
@@ -71,13 +82,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned stage buffers
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int STAGES = GemmCfg<G>::STAGES, STAGE_BYTES = GemmCfg<G>::STAGE_BYTES;
     uint8_t* staging_base = smem + STAGES * STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + EPI_WARPS * STAGING_BYTES);
-    uint64_t* full_bar = bars;                   // [STAGES]  TMA -> MMA
-    uint64_t* empty_bar = bars + STAGES;         // [STAGES]  MMA -> TMA
-    uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]       MMA -> epilogue
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]     epilogue -> MMA
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* full_bar = bars;                       // [STAGES]  TMA -> MMA (G = 2: the leader's, fed by both CTAs)
+    uint64_t* empty_bar = bars + MAX_STAGES;         // [STAGES]  MMA -> TMA (G = 2: multicast commit to both CTAs)
+    uint64_t* tfull_bar = bars + 2 * MAX_STAGES;     // [2]       MMA -> epilogue (G = 2: multicast)
+    uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;  // [2]     epilogue -> MMA (G = 2: both CTAs' warps arrive on the leader's)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+    // rank of this CTA in its pair (0 = leader: issues the MMAs); work is distributed over pairs
+    const int rank = G == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int unit = static_cast<int>(blockIdx.x) / G, num_units = static_cast<int>(gridDim.x) / G;
 
     // warp index through a shuffle: provably warp-uniform, so per-warp addresses / coordinates live in uniform registers
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -96,16 +111,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], EPI_WARPS);
+            mbar_init(&tempty_bar[a], EPI_WARPS * G);
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-        tmem_relinquish();
+        if (G == 1) {
+            tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+            tmem_relinquish();
+        } else {
+            tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+            tmem_relinquish_pair();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (G == 1)
+        __syncthreads();
+    else
+        cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / complete_tx
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -119,27 +142,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // =========================== TMA producer ===========================
         int stage = 0;
         uint32_t phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const WorkItem it = decode_work(p, w);
+        auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+            if (G == 1)
+                tma_load_2d(dst, map, bar, c0, c1);
+            else
+                tma_load_2d_pair(dst, map, bar, c0, c1);
+        };
+        for (int w = unit; w < total_work; w += num_units) {
+            const WorkItem it = decode_work<G>(p, w, rank);
+            const int n0 = it.n_blk * BN + rank * (BN / G);  // this CTA's share of the B tile
             for (int kb = it.kb0; kb < it.kb1; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                 uint8_t* sa = smem + stage * STAGE_BYTES;
                 uint8_t* sb = sa + A_STAGE_BYTES;
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES * G);
                     if (A_MN == 0) {
-                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, it.m_blk * BM);
+                        load(sa, &tmA, &full_bar[stage], kb * BK, it.m_blk * BM);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BM / 64; ++i)
-                            tma_load_2d(sa + i * (64 * BK * 2), &tmA, &full_bar[stage], it.m_blk * BM + i * 64, kb * BK);
+                            load(sa + i * (64 * BK * 2), &tmA, &full_bar[stage], it.m_blk * BM + i * 64, kb * BK);
                     }
                     if (B_MN == 0) {
-                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, it.n_blk * BN);
+                        load(sb, &tmB, &full_bar[stage], kb * BK, n0);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            tma_load_2d(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], it.n_blk * BN + i * 64, kb * BK);
+                        for (int i = 0; i < BN / G / 64; ++i)
+                            load(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
                     }
                 }
                 __syncwarp();
@@ -149,9 +179,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
-        constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    } else if (warp == 1 && rank == 0) {
+        // =========================== MMA issuer (leader CTA only when G = 2) ===========================
+        constexpr uint32_t idesc = make_idesc_bf16(BM * G, BN, A_MN, B_MN);
         // descriptor = constant high word (SBO 1024 B, version 1, SWIZZLE_128B) + low word (address, LBO)
         constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
         constexpr uint32_t lbo_a = A_MN == 0 ? 16u : (64u * BK * 2u), lbo_b = B_MN == 0 ? 16u : (64u * BK * 2u);
@@ -161,8 +191,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const WorkItem it = decode_work(p, w);
+        for (int w = unit; w < total_work; w += num_units) {
+            const WorkItem it = decode_work<G>(p, w, rank);
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BN;
@@ -176,10 +206,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t first = kb > it.kb0 ? 1u : 0u;
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_bf16_ss(tmem_d, make_desc(a_lo + k * kstep_a, desc_hi), make_desc(b_lo + k * kstep_b, desc_hi), idesc,
-                                     k > 0 ? 1u : first);
-                    umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (G == 1)
+                            umma_bf16_ss(tmem_d, make_desc(a_lo + k * kstep_a, desc_hi), make_desc(b_lo + k * kstep_b, desc_hi),
+                                         idesc, k > 0 ? 1u : first);
+                        else
+                            umma_bf16_ss_pair(tmem_d, make_desc(a_lo + k * kstep_a, desc_hi),
+                                              make_desc(b_lo + k * kstep_b, desc_hi), idesc, k > 0 ? 1u : first);
+                    }
+                    // smem slot is free once these MMAs have read it (G = 2: in both CTAs)
+                    if (G == 1)
+                        umma_commit(&empty_bar[stage]);
+                    else
+                        umma_commit_pair(&empty_bar[stage]);
                 }
                 __syncwarp();
                 if (++stage == STAGES) {
@@ -187,7 +226,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     phase ^= 1;
                 }
             }
-            if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete
+            if (elect_one()) {  // accumulator complete
+                if (G == 1)
+                    umma_commit(&tfull_bar[acc]);
+                else
+                    umma_commit_pair(&tfull_bar[acc]);
+            }
             __syncwarp();
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -203,8 +247,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         int buf = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const WorkItem it = decode_work(p, w);
+        for (int w = unit; w < total_work; w += num_units) {
+            const WorkItem it = decode_work<G>(p, w, rank);
             const int row0 = it.m_blk * BM + q * 32;
             const int row = row0 + lane;
             const int colbase = it.n_blk * BN + hf * 128;
@@ -222,11 +266,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             };
             load_aux(aux_cur, colbase);  // issued before the accumulator wait: latency hides behind the MMA
-            if (has_aux && w + (int)gridDim.x < total_work) {
+            if (has_aux && w + num_units < total_work) {
                 // The aux rows of this CTA's NEXT tile go to L2 now: a whole main loop ahead of their use, so the
                 // per-chunk loads above hit L2 (~300 cycles) instead of HBM (~1500), which had made the short-K
                 // residual / GELU' epilogues latency-bound (proj forward: 136 us against 93 us without epilogue).
-                const WorkItem nx = decode_work(p, w + gridDim.x);
+                const WorkItem nx = decode_work<G>(p, w + num_units, rank);
                 const int nrow = nx.m_blk * BM + q * 32 + lane, ncol = nx.n_blk * BN + hf * 128;
                 if (nrow < p.M && ncol < p.N) {
                     const bf16* pa = p.aux + (long long)nrow * p.ld_aux + ncol;
@@ -246,7 +290,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + hf * 128 + c * 32, v);
                 if (c < 3) load_aux(aux_nxt, col0 + 32);
                 tmem_ld_wait();
-                if (col0 < p.N) {
+                if (col0 < p.N && row0 < p.M) {  // (G = 2: the odd CTA's rows of the last tile may all lie beyond M)
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -317,13 +361,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             }
                         } else if (epi == VB_EPI_BF16_GELU_GRAD) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float g0, d0, g1, d1;
-                                gelu_and_grad_erf(f[2 * j], g0, d0);
-                                gelu_and_grad_erf(f[2 * j + 1], g1, d1);
-                                o[j] = pack_bf16x2(g0, g1);
-                                o2[j] = pack_bf16x2(d0, d1);
-                            }
+                            for (int j = 0; j < 16; ++j) gelu_and_grad_erf_x2(f[2 * j], f[2 * j + 1], o[j], o2[j]);
                         } else if (epi == VB_EPI_BF16_GELU) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
@@ -400,7 +438,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // all tcgen05.ld of this accumulator have completed (wait::ld above): hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (elect_one()) mbar_arrive(&tempty_bar[acc]);
+            if (elect_one()) {
+                if (G == 1)
+                    mbar_arrive(&tempty_bar[acc]);
+                else
+                    mbar_arrive_leader(&tempty_bar[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
 
@@ -421,32 +464,64 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (G == 1)
+        __syncthreads();
+    else
+        cluster_sync_all();  // neither CTA may leave (or free TMEM) while the pair's MMAs / remote arrives are in flight
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (G == 1)
+            tmem_dealloc(tmem_base, TMEM_COLS);
+        else
+            tmem_dealloc_pair(tmem_base, TMEM_COLS);
     }
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int G>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                        const GemmKernelParams& p, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     VB_CHECK_CUDA(cudaGetDevice(&dev));
-    auto kern = gemm_tcgen05_kernel<A_MN, B_MN>;
+    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, G>;
     if (dev < 64 && !attr_set[dev]) {
         VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         attr_set[dev] = true;
     }
     const int total_work = p.num_m_blocks * p.num_n_blocks * p.split_k;
-    const int grid = total_work < num_sms() ? total_work : num_sms();
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p);
+    const int units = num_sms() / G;  // CTAs (G = 1) or CTA pairs (G = 2) resident at once
+    const int grid = (total_work < units ? total_work : units) * G;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = G > 1 ? 1 : 0;
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p));
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
 
+// 1 = CTA pairs (256 x 256 tiles, cta_group::2), 0 = single CTAs (128 x 256). Default from VB_GEMM_CTA_PAIR (1 if unset).
+static int g_cta_pair = -1;
+static int cta_pair_enabled() {
+    if (g_cta_pair < 0) {
+        const char* e = getenv("VB_GEMM_CTA_PAIR");
+        g_cta_pair = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return g_cta_pair;
+}
+
 }  // namespace vb
+
+extern "C" void vb_set_gemm_cta_pair(int enabled) { vb::g_cta_pair = enabled ? 1 : 0; }
+extern "C" int vb_get_gemm_cta_pair(void) { return vb::cta_pair_enabled(); }
 
 extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     using namespace vb;
@@ -460,7 +535,29 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
                  a->epilogue);
     VB_CHECK_ARG(a->n % 8 == 0, "vb_gemm_bf16: n=%d must be a multiple of 8", a->n);
     const int epi = a->epilogue;
-    const int split_k = a->split_k < 1 ? 1 : a->split_k;
+    // a CTA pair per 256 x 256 tile whenever there is more than one 128-row block to pair up
+    const int G = (cta_pair_enabled() && a->m > BM) ? 2 : 1;
+    const int m_tiles = (a->m + BM * G - 1) / (BM * G), n_tiles = (a->n + BN - 1) / BN, k_blocks = (a->k + BK - 1) / BK;
+    int split_k = a->split_k;
+    if (split_k <= 0) {
+        // auto (VB_EPI_F32_ADD only): the smallest split whose work items fill >= 90 % of the CTAs / pairs of its last
+        // wave (fewer splits = fewer fp32 reduce-adds), else the best-filling one; at least 8 k-blocks per split
+        split_k = 1;
+        if (epi == VB_EPI_F32_ADD) {
+            const int units = num_sms() / G, tiles = m_tiles * n_tiles;
+            const int max_split = k_blocks / 8 < 1 ? 1 : (k_blocks / 8 > 64 ? 64 : k_blocks / 8);
+            double best = 0.0;
+            for (int s = 1; s <= max_split; ++s) {
+                const int work = tiles * s, waves = (work + units - 1) / units;
+                const double fill = static_cast<double>(work) / (static_cast<double>(waves) * units);
+                if (fill > best + 1e-9) {
+                    best = fill;
+                    split_k = s;
+                }
+                if (fill >= 0.9) break;
+            }
+        }
+    }
     VB_CHECK_ARG(split_k == 1 || epi == VB_EPI_F32_ADD, "vb_gemm_bf16: split_k > 1 needs VB_EPI_F32_ADD");
     if (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX)
         VB_CHECK_ARG(a->aux != nullptr && a->ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,
@@ -487,7 +584,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
                                 CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (a->b_layout == 0)
-        rc = make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, a->k, a->n, a->ldb * 2, BK, BN,
+        rc = make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, a->k, a->n, a->ldb * 2, BK, BN / G,
                                 CU_TENSOR_MAP_SWIZZLE_128B);
     else
         rc = make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, a->n, a->k, a->ldb * 2, 64, BK,
@@ -518,9 +615,9 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     p.M = a->m;
     p.N = a->n;
     p.K = a->k;
-    p.num_m_blocks = (a->m + BM - 1) / BM;
-    p.num_n_blocks = (a->n + BN - 1) / BN;
-    p.num_k_blocks = (a->k + BK - 1) / BK;
+    p.num_m_blocks = m_tiles;
+    p.num_n_blocks = n_tiles;
+    p.num_k_blocks = k_blocks;
     int sk = split_k > p.num_k_blocks ? p.num_k_blocks : split_k;
     p.kb_per_split = (p.num_k_blocks + sk - 1) / sk;
     p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // every split is non-empty
@@ -535,8 +632,14 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     p.has_out2 = a->out2 != nullptr;
     p.out_colsum = a->out_colsum;
 
-    if (a->a_layout == 0 && a->b_layout == 0) return launch_gemm<0, 0>(tmA, tmB, tmC, tmC2, p, stream);
-    if (a->a_layout == 0 && a->b_layout == 1) return launch_gemm<0, 1>(tmA, tmB, tmC, tmC2, p, stream);
-    if (a->a_layout == 1 && a->b_layout == 1) return launch_gemm<1, 1>(tmA, tmB, tmC, tmC2, p, stream);
-    return launch_gemm<1, 0>(tmA, tmB, tmC, tmC2, p, stream);
+    if (G == 2) {
+        if (a->a_layout == 0 && a->b_layout == 0) return launch_gemm<0, 0, 2>(tmA, tmB, tmC, tmC2, p, stream);
+        if (a->a_layout == 0 && a->b_layout == 1) return launch_gemm<0, 1, 2>(tmA, tmB, tmC, tmC2, p, stream);
+        if (a->a_layout == 1 && a->b_layout == 1) return launch_gemm<1, 1, 2>(tmA, tmB, tmC, tmC2, p, stream);
+        return launch_gemm<1, 0, 2>(tmA, tmB, tmC, tmC2, p, stream);
+    }
+    if (a->a_layout == 0 && a->b_layout == 0) return launch_gemm<0, 0, 1>(tmA, tmB, tmC, tmC2, p, stream);
+    if (a->a_layout == 0 && a->b_layout == 1) return launch_gemm<0, 1, 1>(tmA, tmB, tmC, tmC2, p, stream);
+    if (a->a_layout == 1 && a->b_layout == 1) return launch_gemm<1, 1, 1>(tmA, tmB, tmC, tmC2, p, stream);
+    return launch_gemm<1, 0, 1>(tmA, tmB, tmC, tmC2, p, stream);
 }

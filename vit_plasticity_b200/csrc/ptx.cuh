@@ -159,6 +159,60 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ----------------------------------------------------------------------------------------------
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): the even CTA of the pair ("leader") issues the MMAs for both SMs.
+// In the shared::cluster window of a pair, bit 24 of a shared::cta address selects the odd CTA; clearing it addresses the
+// same offset in the leader (the convention of cute's Sm100MmaPeerBitMask).
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in the LEADER CTA of the pair (works from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+// TMA load into THIS CTA's smem whose bytes are counted on the LEADER's mbarrier (both CTAs of a pair feed one MMA)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (128 rows from each CTA's smem) * B (N/2 columns from each CTA's smem); M = 256
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all prior MMAs of the pair arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+
 // 32 lanes x 32 columns of 32-bit: thread t of the warp gets lane (32*(warp%4)+t), columns [c, c+32)
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -276,6 +330,66 @@ __device__ __forceinline__ void gelu_and_grad_erf(float z, float& g, float& dg) 
     g = fmaf(-fabsf(z), h, fmaxf(z, 0.f));
     const float cdf = z >= 0.f ? 1.0f - h : h;
     dg = fmaf(z * 0.3989422804014327f, e, cdf);
+}
+
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issued instruction) ----
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t splat_f32x2(float c) { return pack_f32x2(c, c); }
+
+// gelu and gelu' of two pre-activations at once, same formulas as gelu_and_grad_erf (A&S 7.1.26, |err| <= 1.5e-7), with
+// every multiply-add issued as a packed f32x2 instruction: 15 FMA-pipe instructions per PAIR instead of 15 per element.
+// Phi(z) = 0.5 + sign(z) (0.5 - h),  h = 0.5 erfc(|z| / sqrt 2);  outputs packed to bf16x2: g = (gelu(z0), gelu(z1)).
+__device__ __forceinline__ void gelu_and_grad_erf_x2(float z0, float z1, uint32_t& g_bf16x2, uint32_t& dg_bf16x2) {
+    const uint64_t z = pack_f32x2(z0, z1);
+    const uint64_t naz = pack_f32x2(__uint_as_float(__float_as_uint(z0) | 0x80000000u),
+                                    __uint_as_float(__float_as_uint(z1) | 0x80000000u));  // -|z|
+    const uint64_t u = fma_f32x2(naz, splat_f32x2(-0.3275911f * 0.70710678118654752f), splat_f32x2(1.0f));
+    float u0, u1;
+    unpack_f32x2(u, u0, u1);
+    const uint64_t t = pack_f32x2(fast_rcp(u0), fast_rcp(u1));
+    const uint64_t w = mul_f32x2(mul_f32x2(z, splat_f32x2(-0.72134752044448170f)), z);
+    float w0, w1;
+    unpack_f32x2(w, w0, w1);
+    const uint64_t e = pack_f32x2(fast_ex2(w0), fast_ex2(w1));  // exp(-z^2 / 2)
+    uint64_t poly = fma_f32x2(splat_f32x2(0.5f * 1.061405429f), t, splat_f32x2(0.5f * -1.453152027f));
+    poly = fma_f32x2(poly, t, splat_f32x2(0.5f * 1.421413741f));
+    poly = fma_f32x2(poly, t, splat_f32x2(0.5f * -0.284496736f));
+    poly = fma_f32x2(poly, t, splat_f32x2(0.5f * 0.254829592f));
+    const uint64_t h = mul_f32x2(mul_f32x2(poly, t), e);
+    const uint64_t relu = pack_f32x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+    const uint64_t g = fma_f32x2(naz, h, relu);  // relu(z) - |z| h
+    const uint64_t q = fma_f32x2(h, splat_f32x2(-1.0f), splat_f32x2(0.5f));  // 0.5 - h
+    const uint64_t sgn = pack_f32x2(__uint_as_float((__float_as_uint(z0) & 0x80000000u) | 0x3f800000u),
+                                    __uint_as_float((__float_as_uint(z1) & 0x80000000u) | 0x3f800000u));
+    const uint64_t cdf = fma_f32x2(sgn, q, splat_f32x2(0.5f));
+    const uint64_t dg = fma_f32x2(mul_f32x2(z, splat_f32x2(0.3989422804014327f)), e, cdf);
+    float a0, a1;
+    unpack_f32x2(g, a0, a1);
+    g_bf16x2 = pack_bf16x2(a0, a1);
+    unpack_f32x2(dg, a0, a1);
+    dg_bf16x2 = pack_bf16x2(a0, a1);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

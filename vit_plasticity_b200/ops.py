@@ -94,13 +94,6 @@ def _f32c(p: torch.Tensor | None) -> torch.Tensor | None:
     return d if d.is_contiguous() else d.contiguous()
 
 
-def _wgrad_split_k(n_out: int, k_in: int, tokens: int) -> int:
-    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
-    kb = (tokens + 63) // 64
-    sk = max(1, (2 * NUM_SMS) // tiles)
-    return max(1, min(sk, kb // 8 if kb >= 8 else 1))
-
-
 # --------------------------------------------------------------------------------------------------
 # functional building blocks (no autograd); x / dy are bf16 [tokens, features], contiguous
 # --------------------------------------------------------------------------------------------------
@@ -143,7 +136,7 @@ def linear_wgrad(dy, x, shape, param=None):
     k_in = x.shape[1]
     tgt = grad_target(param)
     dw = tgt.view(n_out, k_in) if tgt is not None else torch.zeros(n_out, k_in, device=dy.device, dtype=torch.float32)
-    L.gemm(dy, x, m=n_out, n=k_in, k=tokens, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=_wgrad_split_k(n_out, k_in, tokens))
+    L.gemm(dy, x, m=n_out, n=k_in, k=tokens, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=0)  # 0: the library picks the split that fills the SMs
     if tgt is not None:
         grad_done(param)
         return None
