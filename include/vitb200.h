@@ -88,10 +88,11 @@ typedef struct vb_gemm_args {
 } vb_gemm_args;
 
 int vb_gemm_bf16(const vb_gemm_args* args, vb_stream_t stream);
-/* Tile mapping of vb_gemm_bf16: 1 (default; env VB_GEMM_CTA_PAIR=0 turns it off) = a CTA pair per 256 x 256 tile with
- * tcgen05.mma.cta_group::2 (each SM stages half of the B tile), 0 = one CTA per 128 x 256 tile. Results are bit-identical
- * per output element for split_k == 1 (same k order); the setting exists for measurement and bisection. */
-void vb_set_gemm_cta_pair(int enabled);
+/* Tile mapping of vb_gemm_bf16: 1 (default; env VB_GEMM_CTA_PAIR=0..3 overrides) = a CTA pair per 256 x 256 tile with
+ * tcgen05.mma.cta_group::2 (each SM stages half of the B tile), 0 = one CTA per 128 x 256 tile; 2 / 3 = pairs with the
+ * 6-stage / 5-stage shared-memory split forced for every epilogue. Results are bit-identical per output element for
+ * split_k == 1 (same k order); the setting exists for measurement and bisection. */
+void vb_set_gemm_cta_pair(int mode);
 int vb_get_gemm_cta_pair(void);
 
 /* ------------------------------------------------------------------------------------------------

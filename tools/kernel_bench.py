@@ -1,5 +1,6 @@
 """Per-kernel timings at the ViT-B/16 batch-512 shapes (CUDA events, L2 flushed between timed iterations)."""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -33,11 +34,29 @@ def timeit(fn, iters=10, warm=3):
     return ts[len(ts) // 2]
 
 
+MODES = [int(c) for c in os.environ.get("KB_GEMM_MODES", "")] if os.environ.get("KB_GEMM_MODES") else None
+MODE_NAMES = {0: "single", 1: "pair", 2: "pair/6-stage", 3: "pair/5-stage"}
+
+
+def timeit_gemm(name, fn, flops):
+    """Times a GEMM call; with KB_GEMM_MODES (e.g. "1230") once per tile mapping, back to back on the same operands, so
+    the variants are compared under the same clocks / temperature."""
+    if not MODES:
+        report(name, timeit(fn), flops=flops)
+        return
+    before = L.lib().vb_get_gemm_cta_pair()
+    parts = []
+    for mode in MODES:
+        L.lib().vb_set_gemm_cta_pair(mode)
+        ms = timeit(fn)
+        parts.append(f"{MODE_NAMES[mode]} {ms*1e3:7.1f} us ({flops / ms / 1e9:6.0f} TF)")
+    L.lib().vb_set_gemm_cta_pair(before)
+    print(f"{name:34s} " + " | ".join(parts), flush=True)
+
+
 def rnd(*s, dt=torch.bfloat16, scale=1.0):
     return (torch.randn(*s, device=dev) * scale).to(dt)
 
-
-import os  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 GEMM_ONLY = os.environ.get("KB_ONLY") == "gemm"
@@ -66,8 +85,7 @@ for name, n, k, epi in [("fwd qkv  bias", F3, E, L.EPI_BF16), ("fwd proj bias+re
     out = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
     out2 = torch.empty(M, n, device=dev, dtype=torch.bfloat16) if epi in (L.EPI_BF16_GELU, L.EPI_BF16_GELU_GRAD) else None
     aux = rnd(M, n) if epi == L.EPI_BF16_RESID else None
-    ms = timeit(lambda: L.gemm(a, w, m=M, n=n, k=k, epilogue=epi, bias=bias, aux=aux, out=out, out2=out2))
-    report(name, ms, flops=2.0 * M * n * k)
+    timeit_gemm(name, lambda: L.gemm(a, w, m=M, n=n, k=k, epilogue=epi, bias=bias, aux=aux, out=out, out2=out2), 2.0 * M * n * k)
     ref = timeit(lambda: torch.nn.functional.linear(a, w))
     report("   (torch F.linear bf16, no epi)", ref, flops=2.0 * M * n * k)
     del a, w, out, out2, aux
@@ -77,14 +95,11 @@ for name, n_out, k_in, epi in [("dgrad fc2 (+dgelu)", E, FF, L.EPI_BF16_DGELU), 
     w = rnd(n_out, k_in, scale=0.02)
     z = rnd(M, k_in) if epi == L.EPI_BF16_DGELU else None
     out = torch.empty(M, k_in, device=dev, dtype=torch.bfloat16)
-    ms = timeit(lambda: L.gemm(dy, w, m=M, n=k_in, k=n_out, b_layout=1, epilogue=epi, aux=z, out=out))
-    report(name, ms, flops=2.0 * M * n_out * k_in)
+    timeit_gemm(name, lambda: L.gemm(dy, w, m=M, n=k_in, k=n_out, b_layout=1, epilogue=epi, aux=z, out=out), 2.0 * M * n_out * k_in)
     if epi == L.EPI_BF16_DGELU:  # the training path: saved derivative, one multiply; optionally + fused column sums (fc1 bias grad)
-        ms = timeit(lambda: L.gemm(dy, w, m=M, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out))
-        report("dgrad fc2 (x saved gelu')", ms, flops=2.0 * M * n_out * k_in)
+        timeit_gemm("dgrad fc2 (x saved gelu')", lambda: L.gemm(dy, w, m=M, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out), 2.0 * M * n_out * k_in)
         cs = torch.zeros(k_in, device=dev)
-        ms = timeit(lambda: L.gemm(dy, w, m=M, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out, out_colsum=cs))
-        report("dgrad fc2 (x gelu' + colsum)", ms, flops=2.0 * M * n_out * k_in)
+        timeit_gemm("dgrad fc2 (x gelu' + colsum)", lambda: L.gemm(dy, w, m=M, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out, out_colsum=cs), 2.0 * M * n_out * k_in)
     del dy, w, z, out
 
 for name, n_out, k_in in [("wgrad fc1", FF, E), ("wgrad fc2", E, FF), ("wgrad qkv", F3, E), ("wgrad proj", E, E)]:
@@ -92,10 +107,9 @@ for name, n_out, k_in in [("wgrad fc1", FF, E), ("wgrad fc2", E, FF), ("wgrad qk
     xx = rnd(M, k_in)
     dw = torch.zeros(n_out, k_in, device=dev)
     tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
-    for waves in (0, 1, 2, 4):
+    for waves in ((0,) if MODES else (0, 1, 2, 4)):
         sk = max(1, (148 * waves) // tiles) if waves else 0  # 0: the library's own choice
-        ms = timeit(lambda: L.gemm(dy, xx, m=n_out, n=k_in, k=M, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=sk))
-        report(f"{name} split_k={sk}", ms, flops=2.0 * M * n_out * k_in)
+        timeit_gemm(f"{name} split_k={sk}", lambda: L.gemm(dy, xx, m=n_out, n=k_in, k=M, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=sk), 2.0 * M * n_out * k_in)
     ref = timeit(lambda: torch.matmul(dy.T, xx))
     report("   (torch matmul dy^T x)", ref, flops=2.0 * M * n_out * k_in)
     del dy, xx, dw

@@ -7,10 +7,10 @@
 using namespace vb;
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) gelu_kernel(const float* __restrict__ in, uint32_t* out, int reps, long long* cyc) {
+__global__ void __launch_bounds__(512, 1) gelu_kernel(const float* __restrict__ in, uint32_t* out, int reps, long long* cyc) {
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = in[threadIdx.x * 32 + j];
+    for (int j = 0; j < 32; ++j) f[j] = in[(threadIdx.x & 255) * 32 + j];
     uint32_t acc = 0, acc2 = 0;
     __syncthreads();
     const long long t0 = clock64();
@@ -80,7 +80,7 @@ int main() {
     uint32_t* out;
     long long* cyc;
     cudaMalloc(&in, 256 * 32 * 4);
-    cudaMalloc(&out, (148 * 256 + 2) * 4);
+    cudaMalloc(&out, (148 * 512 + 2) * 4);
     cudaMalloc(&cyc, 148 * 8);
     float h[256 * 32];
     for (int i = 0; i < 256 * 32; ++i) h[i] = ((i * 2654435761u) % 8000) / 1000.f - 4.f;
@@ -99,6 +99,13 @@ int main() {
         return (double)mx / reps;
     };
     for (int it = 0; it < 2; ++it) {
+        for (int nt = 128; nt <= 512; nt *= 2) {
+            gelu_kernel<0><<<148, nt>>>(in, out, reps, cyc);
+            double a = report("gelu+gelu' scalar fp32", 1);
+            gelu_kernel<1><<<148, nt>>>(in, out, reps, cyc);
+            double b = report("gelu+gelu' packed f32x2", 1);
+            printf("  -> %d warps/SM: math of one 128x256 tile (32 chunks): scalar %.0f clk, packed %.0f clk\n", nt / 32, a * 32 / (nt / 32), b * 32 / (nt / 32));
+        }
         gelu_kernel<0><<<148, 256>>>(in, out, reps, cyc);
         double a = report("gelu+gelu' scalar fp32", 1);
         gelu_kernel<1><<<148, 256>>>(in, out, reps, cyc);

@@ -12,6 +12,7 @@
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
 // warps 4..11 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the 128-column half of the tile).
 #include "host_utils.h"
+#define VB_MBAR_TRAP_PRINTF 0  // no CALL in this kernel: see ptx.cuh (per-role register budgets via setmaxnreg)
 #include "ptx.cuh"
 
 namespace vb {
@@ -24,20 +25,25 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 // G = CTAs per tile: 1 = one CTA computes 128 x 256 (cta_group::1); 2 = a CTA pair computes 256 x 256 with ONE
 // tcgen05.mma.cta_group::2 per k-step: each CTA stages its own 128 rows of A and only HALF of the B tile (128 columns),
 // so the smem operand traffic per SM per MMA drops from 12 KB to 8 KB and the ring holds 6 stages instead of 4.
-template <int G>
+// DEEP (pairs only) trades one ring stage for twice the epilogue staging: 5 x 32 KB + 8 x 8 KB instead of 6 x 32 KB +
+// 8 x 4 KB, so a two-output (GELU + GELU') chunk or an fp32 chunk is double-buffered against its TMA store.
+template <int G, int DEEP>
 struct GemmCfg {
     static constexpr int B_STAGE_BYTES = (BN / G) * BK * 2;  // 32 KB / 16 KB
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = G == 1 ? 4 : 6;
+    static constexpr int STAGES = G == 1 ? 4 : (DEEP ? 5 : 6);
+    // per epilogue warp: 2 KB buffers (32 rows x 64 B bf16; an fp32 chunk or a two-output chunk takes two)
+    static constexpr int STAGING_BYTES = (G == 2 && DEEP) ? 8192 : 4096;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * STAGING_BYTES + 256 + 1024;  // + barriers + alignment slack
 };
 constexpr int MAX_STAGES = 6;
+
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_FIRST_WARP = 4;
-constexpr int STAGING_BYTES = 4096;  // per epilogue warp: 2 x (32 rows x 64 B) bf16 or 1 x (32 rows x 128 B) f32
 constexpr int GEMM_THREADS = (EPI_FIRST_WARP + EPI_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_SMEM_BYTES = 4 * 49152 + EPI_WARPS * STAGING_BYTES + 256 + 1024;  // ring (4 x 48 KB = 6 x 32 KB) + staging + barriers + align
-static_assert(GemmCfg<1>::STAGES * GemmCfg<1>::STAGE_BYTES == 4 * 49152 && GemmCfg<2>::STAGES * GemmCfg<2>::STAGE_BYTES == 4 * 49152, "ring size");
+static_assert(GemmCfg<1, 0>::SMEM_BYTES <= 232448 && GemmCfg<2, 0>::SMEM_BYTES <= 232448 && GemmCfg<2, 1>::SMEM_BYTES <= 232448,
+              "dynamic smem limit of sm_100");
 
 struct GemmKernelParams {
     int M, N, K;
@@ -74,7 +80,8 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKernelParams& p, int w
     return it;
 }
 
-template <int A_MN, int B_MN, int G>
+// EPI_T >= 0: the epilogue is fixed at compile time (the hot combinations); -1: taken from p.epi at run time.
+template <int A_MN, int B_MN, int G, int EPI_T, int DEEP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
@@ -82,9 +89,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned stage buffers
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int STAGES = GemmCfg<G>::STAGES, STAGE_BYTES = GemmCfg<G>::STAGE_BYTES;
+    using Cfg = GemmCfg<G, DEEP>;
+    constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int STAGING = Cfg::STAGING_BYTES, NBUF = STAGING / 2048;
     uint8_t* staging_base = smem + STAGES * STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + EPI_WARPS * STAGING_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + EPI_WARPS * STAGING);
     uint64_t* full_bar = bars;                       // [STAGES]  TMA -> MMA (G = 2: the leader's, fed by both CTAs)
     uint64_t* empty_bar = bars + MAX_STAGES;         // [STAGES]  MMA -> TMA (G = 2: multicast commit to both CTAs)
     uint64_t* tfull_bar = bars + 2 * MAX_STAGES;     // [2]       MMA -> epilogue (G = 2: multicast)
@@ -131,6 +140,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / complete_tx
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // The launch gives every thread 168 registers; the TMA / MMA warpgroup needs few, the two epilogue warpgroups hold two
+    // 32-register accumulator chunks plus the epilogue operands: 128 x 56 + 256 x 224 = 64 512 registers.
 
     const int total_work = p.num_m_blocks * p.num_n_blocks * p.split_k;
 
@@ -138,6 +149,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // around the asynchronous instructions: addresses / descriptors stay in uniform registers. (With the whole loop
     // under `if (lane == 0)` the compiler wrapped every UTCHMMA / UTMALDG in a divergence "waterfall" loop of ~20
     // instructions, which made the single issuing thread the bottleneck.)
+    if (warp < EPI_FIRST_WARP) {
+    setmaxnreg_dec<56>();
     if (warp == 0) {
         // =========================== TMA producer ===========================
         int stage = 0;
@@ -236,17 +249,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-    } else if (warp >= EPI_FIRST_WARP) {
+    }
+    } else {
         // =========================== epilogue ===========================
+        setmaxnreg_inc<224>();
+        // Per tile each warp drains a 32-row x 128-column block of the accumulator in four 32-column chunks. The TMEM load
+        // of chunk c + 1 is in flight while chunk c is processed (two register buffers), and the accumulator is handed back
+        // to the MMA warp as soon as the last load has landed, before that chunk's math and stores.
         const int ew = warp - EPI_FIRST_WARP;
         const int q = warp & 3;   // TMEM lane quarter this warp may access
         const int hf = ew >> 2;   // which 128-column half of the tile
-        uint8_t* stg = staging_base + ew * STAGING_BYTES;
-        const int epi = p.epi;
+        uint8_t* stg = staging_base + ew * STAGING;
+        const int epi = EPI_T >= 0 ? EPI_T : p.epi;
         const bool has_aux = (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX);
+        const bool two = (epi == VB_EPI_BF16_GELU || epi == VB_EPI_BF16_GELU_GRAD) && p.has_out2;
+        const bool add_bias = p.bias != nullptr && epi != VB_EPI_F32_ADD && epi != VB_EPI_SUMSQ && epi != VB_EPI_BF16_DGELU &&
+                              epi != VB_EPI_BF16_MULAUX;
         int acc = 0;
         uint32_t acc_phase = 0;
-        int buf = 0;
+        uint32_t ring = 0;  // staging buffers used so far (2 KB units for bf16 chunks, 4 KB for two-output / fp32 chunks)
         for (int w = unit; w < total_work; w += num_units) {
             const WorkItem it = decode_work<G>(p, w, rank);
             const int row0 = it.m_blk * BM + q * 32;
@@ -283,166 +304,187 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
 
             float sumsq_local = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + hf * 128;
+
+            // one 32-column chunk, accumulator values in v (as loaded from TMEM)
+            auto process = [&](uint32_t(&v)[32], const int c) {
                 const int col0 = colbase + c * 32;
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + hf * 128 + c * 32, v);
-                if (c < 3) load_aux(aux_nxt, col0 + 32);
-                tmem_ld_wait();
-                if (col0 < p.N && row0 < p.M) {  // (G = 2: the odd CTA's rows of the last tile may all lie beyond M)
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (p.bias != nullptr && epi != VB_EPI_F32_ADD && epi != VB_EPI_SUMSQ && epi != VB_EPI_BF16_DGELU && epi != VB_EPI_BF16_MULAUX) {
-                        if (col0 + 32 <= p.N) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-                                f[4 * j + 0] += b4.x;
-                                f[4 * j + 1] += b4.y;
-                                f[4 * j + 2] += b4.z;
-                                f[4 * j + 3] += b4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-                        }
-                    }
-                    if (epi == VB_EPI_SUMSQ) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) sumsq_local += f[j] * f[j];
-                    } else if (epi == VB_EPI_F32 || epi == VB_EPI_F32_ADD) {
-                        // 32 rows x 128 B, 16-byte chunk index XOR (row & 7) == TMA SWIZZLE_128B
-                        if (elect_one()) tma_store_wait_read<0>();
-                        __syncwarp();
-                        const uint32_t rowaddr = smem_u32(stg) + lane * 128;
+                if (!(col0 < p.N && row0 < p.M)) return;  // (G = 2: the odd CTA's rows of the last tile may all lie beyond M)
+                float f[32];
+                if (add_bias) {
+                    if (col0 + 32 <= p.N) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const uint32_t a = rowaddr + ((j ^ (lane & 7)) << 4);
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(f[4 * j]),
-                                         "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
-                                         : "memory");
-                        }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (elect_one()) {
-                            if (epi == VB_EPI_F32)
-                                tma_store_2d(&tmC, stg, col0, row0);
-                            else
-                                tma_reduce_add_2d(&tmC, stg, col0, row0);
-                            tma_store_commit();
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                            const uint64_t s0 = add_f32x2(pack_f32x2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                                                          pack_f32x2(b4.x, b4.y));
+                            const uint64_t s1 = add_f32x2(pack_f32x2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
+                                                          pack_f32x2(b4.z, b4.w));
+                            unpack_f32x2(s0, f[4 * j], f[4 * j + 1]);
+                            unpack_f32x2(s1, f[4 * j + 2], f[4 * j + 3]);
                         }
                     } else {
-                        // bf16 outputs: 32 rows x 64 B, chunk index XOR ((row >> 1) & 3) == TMA SWIZZLE_64B
-                        uint32_t o[16], o2[16];
-                        if (epi == VB_EPI_BF16_RESID) {
-                            const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float2 r = unpack_bf16x2(ax[j]);
-                                o[j] = pack_bf16x2(f[2 * j] + r.x, f[2 * j + 1] + r.y);
-                            }
-                        } else if (epi == VB_EPI_BF16_DGELU) {
-                            const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (col0 + j < p.N ? __ldg(p.bias + col0 + j) : 0.f);
+                    }
+                } else {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float2 z = unpack_bf16x2(ax[j]);
-                                o[j] = pack_bf16x2(f[2 * j] * dgelu_erf(z.x), f[2 * j + 1] * dgelu_erf(z.y));
-                            }
-                        } else if (epi == VB_EPI_BF16_MULAUX) {
-                            const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                }
+                if (epi == VB_EPI_SUMSQ) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float2 g = unpack_bf16x2(ax[j]);
-                                o[j] = pack_bf16x2(f[2 * j] * g.x, f[2 * j + 1] * g.y);
-                            }
-                        } else if (epi == VB_EPI_BF16_GELU_GRAD) {
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) sumsq_local += f[j] * f[j];
+                } else if (epi == VB_EPI_F32 || epi == VB_EPI_F32_ADD) {
+                    // 32 rows x 128 B, 16-byte chunk index XOR (row & 7) == TMA SWIZZLE_128B
+                    uint8_t* b0 = stg + (ring % (NBUF / 2)) * 4096;
+                    ++ring;
+                    if (elect_one()) tma_store_wait_read<NBUF / 2 - 1>();
+                    __syncwarp();
+                    const uint32_t rowaddr = smem_u32(b0) + lane * 128;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) gelu_and_grad_erf_x2(f[2 * j], f[2 * j + 1], o[j], o2[j]);
-                        } else if (epi == VB_EPI_BF16_GELU) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                // GELU is applied to the bf16-rounded pre-activation so that forward and the
-                                // saved z used by backward agree exactly
-                                const uint32_t zz = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                                const float2 z = unpack_bf16x2(zz);
-                                o2[j] = zz;
-                                o[j] = pack_bf16x2(gelu_erf(z.x), gelu_erf(z.y));
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                        }
-                        if (p.out_colsum != nullptr) {
-                            // Column sums of this warp's 32 x 32 output block (as rounded to bf16, i.e. exactly what a
-                            // separate pass over the stored tensor would add up): butterfly transpose-reduce over the 32
-                            // lanes (= rows), 31 shuffles, lane c ends with column c; one reduction per column. Replaces a
-                            // full HBM pass over the output (dz of fc1: 620 MB per layer) by ~125 instructions per chunk.
-                            float cs[32];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float2 t = unpack_bf16x2(o[j]);
-                                cs[2 * j] = row_ok ? t.x : 0.f;
-                                cs[2 * j + 1] = row_ok ? t.y : 0.f;
-                            }
-#pragma unroll
-                            for (int off = 16; off >= 1; off >>= 1) {
-                                const bool hi = (lane & off) != 0;
-#pragma unroll
-                                for (int i = 0; i < off; ++i) {
-                                    const float send = hi ? cs[i] : cs[i + off];
-                                    const float keep = hi ? cs[i + off] : cs[i];
-                                    cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                                }
-                            }
-                            if (col0 + lane < p.N) atomicAdd(p.out_colsum + col0 + lane, cs[0]);
-                        }
-                        const bool two = (epi == VB_EPI_BF16_GELU || epi == VB_EPI_BF16_GELU_GRAD) && p.has_out2;
-                        uint8_t* b0 = stg + (two ? 0 : buf * 2048);
-                        if (elect_one()) {
-                            if (two)
-                                tma_store_wait_read<0>();
-                            else
-                                tma_store_wait_read<1>();
-                        }
-                        __syncwarp();
-                        const uint32_t rowaddr = smem_u32(b0) + lane * 64;
-                        const uint32_t sw = (lane >> 1) & 3;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t a = rowaddr + ((j ^ sw) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o[4 * j]),
-                                         "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3])
-                                         : "memory");
-                            if (two)
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(o2[4 * j]),
-                                             "r"(o2[4 * j + 1]), "r"(o2[4 * j + 2]), "r"(o2[4 * j + 3])
-                                             : "memory");
-                        }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (elect_one()) {
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t a = rowaddr + ((j ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(f[4 * j]),
+                                     "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                                     : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        if (epi == VB_EPI_F32)
                             tma_store_2d(&tmC, b0, col0, row0);
-                            if (two) tma_store_2d(&tmC2, b0 + 2048, col0, row0);
-                            tma_store_commit();
+                        else
+                            tma_reduce_add_2d(&tmC, b0, col0, row0);
+                        tma_store_commit();
+                    }
+                } else {
+                    // bf16 outputs: 32 rows x 64 B, chunk index XOR ((row >> 1) & 3) == TMA SWIZZLE_64B
+                    uint32_t o[16], o2[16];
+                    if (epi == VB_EPI_BF16_RESID) {
+                        const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 r = unpack_bf16x2(ax[j]);
+                            o[j] = pack_bf16x2(f[2 * j] + r.x, f[2 * j + 1] + r.y);
                         }
-                        buf ^= 1;
+                    } else if (epi == VB_EPI_BF16_DGELU) {
+                        const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 z = unpack_bf16x2(ax[j]);
+                            o[j] = pack_bf16x2(f[2 * j] * dgelu_erf(z.x), f[2 * j + 1] * dgelu_erf(z.y));
+                        }
+                    } else if (epi == VB_EPI_BF16_MULAUX) {
+                        const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 g = unpack_bf16x2(ax[j]);
+                            o[j] = pack_bf16x2(f[2 * j] * g.x, f[2 * j + 1] * g.y);
+                        }
+                    } else if (epi == VB_EPI_BF16_GELU_GRAD) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) gelu_and_grad_erf_x2(f[2 * j], f[2 * j + 1], o[j], o2[j]);
+                    } else if (epi == VB_EPI_BF16_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            // GELU is applied to the bf16-rounded pre-activation so that forward and the
+                            // saved z used by backward agree exactly
+                            const uint32_t zz = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                            const float2 z = unpack_bf16x2(zz);
+                            o2[j] = zz;
+                            o[j] = pack_bf16x2(gelu_erf(z.x), gelu_erf(z.y));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                    }
+                    if (p.out_colsum != nullptr) {
+                        // Column sums of this warp's 32 x 32 output block (as rounded to bf16, i.e. exactly what a
+                        // separate pass over the stored tensor would add up): butterfly transpose-reduce over the 32
+                        // lanes (= rows), 31 shuffles, lane c ends with column c; one reduction per column. Replaces a
+                        // full HBM pass over the output (dz of fc1: 620 MB per layer) by ~125 instructions per chunk.
+                        float cs[32];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 t = unpack_bf16x2(o[j]);
+                            cs[2 * j] = row_ok ? t.x : 0.f;
+                            cs[2 * j + 1] = row_ok ? t.y : 0.f;
+                        }
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            const bool hi = (lane & off) != 0;
+#pragma unroll
+                            for (int i = 0; i < off; ++i) {
+                                const float send = hi ? cs[i] : cs[i + off];
+                                const float keep = hi ? cs[i + off] : cs[i];
+                                cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                        if (col0 + lane < p.N) atomicAdd(p.out_colsum + col0 + lane, cs[0]);
+                    }
+                    uint8_t* b0;
+                    if (two) {
+                        b0 = stg + (ring % (NBUF / 2)) * 4096;
+                        if (elect_one()) tma_store_wait_read<NBUF / 2 - 1>();
+                    } else {
+                        b0 = stg + (ring % NBUF) * 2048;
+                        if (elect_one()) tma_store_wait_read<NBUF - 1>();
+                    }
+                    ++ring;
+                    __syncwarp();
+                    const uint32_t rowaddr = smem_u32(b0) + lane * 64;
+                    const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t a = rowaddr + ((j ^ sw) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o[4 * j]),
+                                     "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3])
+                                     : "memory");
+                        if (two)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(o2[4 * j]),
+                                         "r"(o2[4 * j + 1]), "r"(o2[4 * j + 2]), "r"(o2[4 * j + 3])
+                                         : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        tma_store_2d(&tmC, b0, col0, row0);
+                        if (two) tma_store_2d(&tmC2, b0 + 2048, col0, row0);
+                        tma_store_commit();
                     }
                 }
+            };
+
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(tacc, va);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < 3) load_aux(aux_nxt, colbase + c * 32 + 32);
+                if ((c & 1) == 0) {
+                    tmem_ld_wait_x32(va);
+                    if (c < 3) tmem_ld_32x32b_x32(tacc + (c + 1) * 32, vb);
+                } else {
+                    tmem_ld_wait_x32(vb);
+                    if (c < 3) tmem_ld_32x32b_x32(tacc + (c + 1) * 32, va);
+                }
+                if (c == 3) {
+                    // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp now
+                    tc_fence_before();
+                    __syncwarp();
+                    if (elect_one()) {
+                        if (G == 1)
+                            mbar_arrive(&tempty_bar[acc]);
+                        else
+                            mbar_arrive_leader(&tempty_bar[acc]);
+                    }
+                }
+                if ((c & 1) == 0)
+                    process(va, c);
+                else
+                    process(vb, c);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) aux_cur[j] = aux_nxt[j];
-            }
-            // all tcgen05.ld of this accumulator have completed (wait::ld above): hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (elect_one()) {
-                if (G == 1)
-                    mbar_arrive(&tempty_bar[acc]);
-                else
-                    mbar_arrive_leader(&tempty_bar[acc]);
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -477,13 +519,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-template <int A_MN, int B_MN, int G>
+template <int A_MN, int B_MN, int G, int EPI_T, int DEEP>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                        const GemmKernelParams& p, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     VB_CHECK_CUDA(cudaGetDevice(&dev));
-    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, G>;
+    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, G, EPI_T, DEEP>;
+    constexpr int GEMM_SMEM_BYTES = GemmCfg<G, DEEP>::SMEM_BYTES;
     if (dev < 64 && !attr_set[dev]) {
         VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         attr_set[dev] = true;
@@ -508,19 +551,21 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     return VB_OK;
 }
 
-// 1 = CTA pairs (256 x 256 tiles, cta_group::2), 0 = single CTAs (128 x 256). Default from VB_GEMM_CTA_PAIR (1 if unset).
+// 0 = single CTAs (128 x 256); 1 = CTA pairs (256 x 256 tiles, cta_group::2) with the ring / staging split chosen per
+// epilogue; 2 / 3 = pairs with the 6-stage / 5-stage split forced everywhere (measurement only).
+// Default from VB_GEMM_CTA_PAIR (1 if unset).
 static int g_cta_pair = -1;
 static int cta_pair_enabled() {
     if (g_cta_pair < 0) {
         const char* e = getenv("VB_GEMM_CTA_PAIR");
-        g_cta_pair = (e != nullptr && e[0] == '0') ? 0 : 1;
+        g_cta_pair = (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 1;
     }
     return g_cta_pair;
 }
 
 }  // namespace vb
 
-extern "C" void vb_set_gemm_cta_pair(int enabled) { vb::g_cta_pair = enabled ? 1 : 0; }
+extern "C" void vb_set_gemm_cta_pair(int mode) { vb::g_cta_pair = (mode >= 0 && mode <= 3) ? mode : 1; }
 extern "C" int vb_get_gemm_cta_pair(void) { return vb::cta_pair_enabled(); }
 
 extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
@@ -536,7 +581,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     VB_CHECK_ARG(a->n % 8 == 0, "vb_gemm_bf16: n=%d must be a multiple of 8", a->n);
     const int epi = a->epilogue;
     // a CTA pair per 256 x 256 tile whenever there is more than one 128-row block to pair up
-    const int G = (cta_pair_enabled() && a->m > BM) ? 2 : 1;
+    const int G = (cta_pair_enabled() != 0 && a->m > BM) ? 2 : 1;
     const int m_tiles = (a->m + BM * G - 1) / (BM * G), n_tiles = (a->n + BN - 1) / BN, k_blocks = (a->k + BK - 1) / BK;
     int split_k = a->split_k;
     if (split_k <= 0) {
@@ -632,14 +677,38 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     p.has_out2 = a->out2 != nullptr;
     p.out_colsum = a->out_colsum;
 
+    // the hot combinations of the training step get an epilogue fixed at compile time, everything else the generic kernel
+#define VB_LAUNCH(AL, BL, GG, EP, DP) return launch_gemm<AL, BL, GG, EP, DP>(tmA, tmB, tmC, tmC2, p, stream)
+#define VB_LAUNCH_PAIR(AL, BL, EP, DP)                     \
+    do {                                                   \
+        if (deep_mode == 0) VB_LAUNCH(AL, BL, 2, EP, 0);   \
+        if (deep_mode == 1) VB_LAUNCH(AL, BL, 2, EP, 1);   \
+        VB_LAUNCH(AL, BL, 2, EP, DP);                      \
+    } while (0)
+    const int al = a->a_layout, bl = a->b_layout;
+    const int deep_mode = cta_pair_enabled() == 2 ? 0 : (cta_pair_enabled() == 3 ? 1 : -1);
     if (G == 2) {
-        if (a->a_layout == 0 && a->b_layout == 0) return launch_gemm<0, 0, 2>(tmA, tmB, tmC, tmC2, p, stream);
-        if (a->a_layout == 0 && a->b_layout == 1) return launch_gemm<0, 1, 2>(tmA, tmB, tmC, tmC2, p, stream);
-        if (a->a_layout == 1 && a->b_layout == 1) return launch_gemm<1, 1, 2>(tmA, tmB, tmC, tmC2, p, stream);
-        return launch_gemm<1, 0, 2>(tmA, tmB, tmC, tmC2, p, stream);
+        if (al == 0 && bl == 0) {
+            if (epi == VB_EPI_BF16) VB_LAUNCH_PAIR(0, 0, VB_EPI_BF16, 0);
+            if (epi == VB_EPI_BF16_RESID) VB_LAUNCH_PAIR(0, 0, VB_EPI_BF16_RESID, 0);
+            if (epi == VB_EPI_BF16_GELU_GRAD) VB_LAUNCH_PAIR(0, 0, VB_EPI_BF16_GELU_GRAD, 1);
+            VB_LAUNCH(0, 0, 2, -1, 0);
+        }
+        if (al == 0 && bl == 1) {
+            if (epi == VB_EPI_BF16) VB_LAUNCH_PAIR(0, 1, VB_EPI_BF16, 0);
+            if (epi == VB_EPI_BF16_MULAUX) VB_LAUNCH_PAIR(0, 1, VB_EPI_BF16_MULAUX, 1);
+            VB_LAUNCH(0, 1, 2, -1, 0);
+        }
+        if (al == 1 && bl == 1) {
+            if (epi == VB_EPI_F32_ADD) VB_LAUNCH_PAIR(1, 1, VB_EPI_F32_ADD, 0);
+            VB_LAUNCH(1, 1, 2, -1, 0);
+        }
+        VB_LAUNCH(1, 0, 2, -1, 0);
     }
-    if (a->a_layout == 0 && a->b_layout == 0) return launch_gemm<0, 0, 1>(tmA, tmB, tmC, tmC2, p, stream);
-    if (a->a_layout == 0 && a->b_layout == 1) return launch_gemm<0, 1, 1>(tmA, tmB, tmC, tmC2, p, stream);
-    if (a->a_layout == 1 && a->b_layout == 1) return launch_gemm<1, 1, 1>(tmA, tmB, tmC, tmC2, p, stream);
-    return launch_gemm<1, 0, 1>(tmA, tmB, tmC, tmC2, p, stream);
+    if (al == 0 && bl == 0) VB_LAUNCH(0, 0, 1, -1, 0);
+    if (al == 0 && bl == 1) VB_LAUNCH(0, 1, 1, -1, 0);
+    if (al == 1 && bl == 1) VB_LAUNCH(1, 1, 1, -1, 0);
+    VB_LAUNCH(1, 0, 1, -1, 0);
+#undef VB_LAUNCH_PAIR
+#undef VB_LAUNCH
 }

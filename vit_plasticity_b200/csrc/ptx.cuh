@@ -63,11 +63,20 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// VB_MBAR_TRAP_PRINTF=0 (set before including this header) drops the diagnostic printf: any CALL in a kernel (printf is
+// one) makes ptxas allocate the WHOLE kernel under its smallest setmaxnreg value, which defeats per-role register budgets.
+#ifndef VB_MBAR_TRAP_PRINTF
+#define VB_MBAR_TRAP_PRINTF 1
+#endif
+#if VB_MBAR_TRAP_PRINTF
 static __device__ __noinline__ void mbar_timeout_trap(int tag, uint32_t parity) {
     printf("[vitb200] mbarrier wait timeout: tag=%d parity=%u block=%d thread=%d\n", tag, parity, (int)blockIdx.x,
            (int)threadIdx.x);
     __trap();
 }
+#else
+__device__ __forceinline__ void mbar_timeout_trap(int, uint32_t) { __trap(); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
     if (mbar_try_wait(bar, parity)) return;
     uint64_t t0 = globaltimer_ns();
@@ -242,6 +251,26 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same, and tells the compiler that the 32 destination registers of an earlier tcgen05.ld change HERE: with other work
+// scheduled between the load and its wait, no copy of those registers made before the wait can be mistaken for the data.
+__device__ __forceinline__ void tmem_ld_wait_x32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+// register reallocation between warpgroups (all four warps of a warpgroup execute the same instruction)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
