@@ -7,7 +7,8 @@ B = 512
 qkv = torch.randn(B * 197, 2304, device="cuda").bfloat16()
 out, lse = L.attention_fwd(qkv, B, 197, 12, 64)
 do = torch.randn(B * 197, 768, device="cuda").bfloat16()
-for name, fn in [("attention_fwd", lambda: L.attention_fwd(qkv, B, 197, 12, 64)), ("attention_bwd", lambda: L.attention_bwd(qkv, out, do, lse, B, 197, 12, 64))]:
+dbias = torch.zeros(2304, device="cuda")
+for name, fn in [("attention_fwd", lambda: L.attention_fwd(qkv, B, 197, 12, 64)), ("attention_bwd", lambda: L.attention_bwd(qkv, out, do, lse, B, 197, 12, 64)), ("attention_bwd + qkv bias grad", lambda: L.attention_bwd(qkv, out, do, lse, B, 197, 12, 64, dbias=dbias))]:
     for _ in range(3):
         fn()
     torch.cuda.synchronize()

@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "host_utils.h"
+#define VB_MBAR_TRAP_PRINTF 0  // no CALL in these kernels: per-role register budgets (setmaxnreg), see ptx.cuh
 #include "ptx.cuh"
 
 namespace vb {
@@ -423,8 +424,9 @@ constexpr int B_SMEM = 2 * B_STAGE + B_TAIL + 1024;
 constexpr uint32_t OFF_Q = 0, OFF_K = OPER_BYTES >> 4, OFF_V = (2 * OPER_BYTES) >> 4, OFF_DO = (3 * OPER_BYTES) >> 4;  // 16-B units
 constexpr uint32_t B_COL_ACC = 384;
 constexpr int GROUP_WARPS = 8;
-constexpr int B_WARP_TMA = 16, B_WARP_MMA1 = 17, B_WARP_MMA2 = 18;
-constexpr int B_THREADS = 19 * 32;
+constexpr int B_WARP_TMA = 16, B_WARP_MMA1 = 17, B_WARP_MMA2 = 18;  // (warp 19 idles: roles are assigned per warpgroup)
+constexpr int B_WARP_DRAIN0 = 20, DRAIN_WARPS = 4;                   // one warp per TMEM lane quarter
+constexpr int B_THREADS = 24 * 32;
 
 __global__ void __launch_bounds__(B_THREADS, 1)
 attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
@@ -469,7 +471,7 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
                 mbar_init(&c_free[i], 1);
             }
             mbar_init(acc_ready, 1);
-            mbar_init(acc_free, GROUP_WARPS);
+            mbar_init(acc_free, DRAIN_WARPS);
             fence_barrier_init();
         }
         __syncwarp();
@@ -482,6 +484,63 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t smem_lo = smem_u32(smem) >> 4;
 
+    // Register budgets per warpgroup, out of the 768 x 80 the launch gives the CTA (setmaxnreg only moves registers inside
+    // that pool): control 32, drain 96, math 88: 128 x 32 + 128 x 96 + 512 x 88 = 61 440.
+    if (warp >= B_WARP_DRAIN0) {
+        // =========================== accumulator drain: dQ / dV,dK rows -> dqkv (+ qkv bias gradient) ===========================
+        // A warpgroup of its own, so that no math warp ever waits for the last MMA2 of a unit: the accumulator is handed
+        // back as soon as its columns are in registers, the global stores and the column sums run behind the next unit.
+        setmaxnreg_inc<96>();
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + B_COL_ACC;
+        const int n_units = 4 * n_local;
+        for (int ug = 0; ug < n_units; ++ug) {
+            const int un = ug & 3;
+            const int it = blockIdx.x + (ug >> 2) * gridDim.x;
+            const int b = it / H, hd = it - b * H;
+            mbar_wait(acc_ready, ug & 1, 74);
+            tc_fence_after();
+            const int r = (un & 1) * 128 + row;  // query (dQ units) or key (dK/dV units)
+            const bool ok = r < L;
+            uint32_t a[32], a2[32];
+            auto release = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_free);
+            };
+            auto put = [&](bf16* dst, float* dcol) {
+                if (ok) {
+                    store_32cols_bf16(dst, a, 1.f);
+                    store_32cols_bf16(dst + 32, a2, 1.f);
+                }
+                if (dbias != nullptr) {
+                    warp_colsum32_atomic(a, ok, dcol, lane);
+                    warp_colsum32_atomic(a2, ok, dcol + 32, lane);
+                }
+            };
+            bf16* drow = dqkv + ((int64_t)b * L + r) * ld3 + hd * HD;
+            tmem_ld_32x32b_x32(acc_addr, a);
+            tmem_ld_32x32b_x32(acc_addr + 32, a2);
+            tmem_ld_wait();
+            reg_fence(a);
+            reg_fence(a2);
+            if (un < 2) {
+                release();
+                put(drow, dbias + hd * HD);  // dQ
+            } else {
+                put(drow + 2 * E, dbias + 2 * E + hd * HD);  // dV (columns [0, 64) of the accumulator)
+                tmem_ld_32x32b_x32(acc_addr + 64, a);
+                tmem_ld_32x32b_x32(acc_addr + 96, a2);
+                tmem_ld_wait();
+                reg_fence(a);
+                reg_fence(a2);
+                release();
+                put(drow + E, dbias + E + hd * HD);  // dK (columns [64, 128))
+            }
+        }
+    } else if (warp >= B_WARP_TMA) {
+    setmaxnreg_dec<32>();
     if (warp == B_WARP_TMA) {
         // =========================== TMA producer (+ lse / delta staging) ===========================
         for (int n = 0; n < n_local; ++n) {
@@ -597,54 +656,16 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
             if (lane == 0) VB_STAMP(g, 2);
             if (++cb == 3) cb = 0, ph ^= 1;
         }
+    }
     } else {
-        // =========================== math warps: group 0 takes even chunks, group 1 odd chunks + accumulator read-out ===========================
+        // =========================== math warps: group 0 takes even chunks, group 1 odd chunks ===========================
+        setmaxnreg_inc<88>();
         const int grp = warp >> 3;
         const int quarter = warp & 3, hf = (warp >> 2) & 1;
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const float c = 0.125f * LOG2E;
         const int c0 = hf * 32;
-
-        auto readout = [&](int ug) {
-            const int un = ug & 3;
-            const int it = blockIdx.x + (ug >> 2) * gridDim.x;
-            const int b = it / H, hd = it - b * H;
-            mbar_wait(acc_ready, ug & 1, 74);
-            tc_fence_after();
-            const int r = (un & 1) * 128 + row;  // query (dQ units) or key (dK/dV units)
-            uint32_t a[32], a2[32];
-            if (un < 2) {
-                tmem_ld_32x32b_x32(lane_addr + B_COL_ACC + hf * 32, a);
-                tmem_ld_wait();
-                reg_fence(a);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_free);
-                if (r < L) store_32cols_bf16(dqkv + ((int64_t)b * L + r) * ld3 + hd * HD + hf * 32, a, 1.f);
-                if (dbias != nullptr) warp_colsum32_atomic(a, r < L, dbias + hd * HD + hf * 32, lane);
-            } else {
-                // column-half 0 warps drain dV, column-half 1 warps drain dK (64 columns each)
-                tmem_ld_32x32b_x32(lane_addr + B_COL_ACC + hf * 64, a);
-                tmem_ld_32x32b_x32(lane_addr + B_COL_ACC + hf * 64 + 32, a2);
-                tmem_ld_wait();
-                reg_fence(a);
-                reg_fence(a2);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_free);
-                if (r < L) {
-                    bf16* dst = dqkv + ((int64_t)b * L + r) * ld3 + (hf == 0 ? 2 * E : E) + hd * HD;
-                    store_32cols_bf16(dst, a, 1.f);
-                    store_32cols_bf16(dst + 32, a2, 1.f);
-                }
-                if (dbias != nullptr) {
-                    float* dcol = dbias + (hf == 0 ? 2 * E : E) + hd * HD;
-                    warp_colsum32_atomic(a, r < L, dcol, lane);
-                    warp_colsum32_atomic(a2, r < L, dcol + 32, lane);
-                }
-            }
-        };
 
         float lse_row = 0.f, dlt_row = 0.f;
         for (int g = grp; g < G; g += 2) {
@@ -747,7 +768,6 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[cb]);
             if (stp) VB_STAMP(g, 8);
-            if (cc == 3) readout(g >> 2);  // (group 1 only: cc == 3 is an odd chunk) the other group keeps the pipes busy meanwhile
             if (stp) VB_STAMP(g, 9);
         }
     }
