@@ -34,7 +34,7 @@ struct GemmCfg {
     static constexpr int STAGES = G == 1 ? 4 : (DEEP ? 5 : 6);
     // per epilogue warp: 2 KB buffers (32 rows x 64 B bf16; an fp32 chunk or a two-output chunk takes two)
     static constexpr int STAGING_BYTES = (G == 2 && DEEP) ? 8192 : 4096;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * STAGING_BYTES + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * STAGING_BYTES + 512 + 1024;  // + barriers + alignment slack
 };
 constexpr int MAX_STAGES = 6;
 
@@ -85,7 +85,7 @@ template <int A_MN, int B_MN, int G, int EPI_T, int DEEP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
-                    const GemmKernelParams p) {
+                    const __grid_constant__ CUtensorMap tmAux, const GemmKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned stage buffers
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -99,6 +99,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tfull_bar = bars + 2 * MAX_STAGES;     // [2]       MMA -> epilogue (G = 2: multicast)
     uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;  // [2]     epilogue -> MMA (G = 2: both CTAs' warps arrive on the leader's)
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+    uint64_t* aux_bar = bars + 2 * MAX_STAGES + 6;   // [EPI_WARPS][4]  TMA (aux chunk) -> epilogue warp, AUX_TMA only
+    // The residual / saved-GELU' operand of the epilogue comes in through TMA, straight into the staging buffer the output
+    // chunk leaves from: two chunks ahead, no per-lane strided global loads, the result overwrites it in place.
+    constexpr bool AUX_TMA = G == 2 && DEEP == 1 && (EPI_T == VB_EPI_BF16_RESID || EPI_T == VB_EPI_BF16_MULAUX);
     // rank of this CTA in its pair (0 = leader: issues the MMAs); work is distributed over pairs
     const int rank = G == 2 ? static_cast<int>(cluster_ctarank()) : 0;
     const int unit = static_cast<int>(blockIdx.x) / G, num_units = static_cast<int>(gridDim.x) / G;
@@ -112,6 +116,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
         tma_prefetch_desc(&tmC2);
+        if (AUX_TMA) tma_prefetch_desc(&tmAux);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -122,6 +127,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], EPI_WARPS * G);
         }
+        if (AUX_TMA)
+            for (int a = 0; a < EPI_WARPS * 4; ++a) mbar_init(&aux_bar[a], 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -268,8 +275,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t ring = 0;  // staging buffers used so far (2 KB units for bf16 chunks, 4 KB for two-output / fp32 chunks)
+        // AUX_TMA: chunk number t (counted over this warp's tiles, 4 per tile) lives in staging buffer t % 4; its aux
+        // operand is requested while chunk t - 2 is processed, after the store that last read the buffer (chunk t - 4).
+        uint64_t* my_aux_bar = aux_bar + ew * 4;
+        auto request_aux = [&](const WorkItem& wi, int c, uint32_t t) {
+            if (elect_one()) {
+                tma_store_wait_read<1>();
+                uint64_t* bar = my_aux_bar + (t & 3);
+                mbar_arrive_expect_tx(bar, 2048);
+                tma_load_2d(stg + (t & 3) * 2048, &tmAux, bar, wi.n_blk * BN + hf * 128 + c * 32, wi.m_blk * BM + q * 32);
+            }
+            __syncwarp();
+        };
+        uint32_t tchunk = 0;
+        if (AUX_TMA && unit < total_work) {
+            const WorkItem first = decode_work<G>(p, unit, rank);
+            request_aux(first, 0, 0);
+            request_aux(first, 1, 1);
+        }
         for (int w = unit; w < total_work; w += num_units) {
             const WorkItem it = decode_work<G>(p, w, rank);
+            const bool have_next = w + num_units < total_work;
+            const WorkItem nxt_it = (AUX_TMA && have_next) ? decode_work<G>(p, w + num_units, rank) : it;
             const int row0 = it.m_blk * BM + q * 32;
             const int row = row0 + lane;
             const int colbase = it.n_blk * BN + hf * 128;
@@ -286,8 +313,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (col0 + j * 8 < p.N) dst[j] = __ldg(reinterpret_cast<const uint4*>(src) + j);
                 }
             };
-            load_aux(aux_cur, colbase);  // issued before the accumulator wait: latency hides behind the MMA
-            if (has_aux && w + num_units < total_work) {
+            if (!AUX_TMA) load_aux(aux_cur, colbase);  // issued before the accumulator wait: latency hides behind the MMA
+            if (!AUX_TMA && has_aux && w + num_units < total_work) {
                 // The aux rows of this CTA's NEXT tile go to L2 now: a whole main loop ahead of their use, so the
                 // per-chunk loads above hit L2 (~300 cycles) instead of HBM (~1500), which had made the short-K
                 // residual / GELU' epilogues latency-bound (proj forward: 136 us against 93 us without epilogue).
@@ -309,6 +336,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // one 32-column chunk, accumulator values in v (as loaded from TMEM)
             auto process = [&](uint32_t(&v)[32], const int c) {
                 const int col0 = colbase + c * 32;
+                uint8_t* abuf = stg + (tchunk & 3) * 2048;  // AUX_TMA: aux chunk in, output chunk out
+                if (AUX_TMA) {
+                    // the aux operand of the chunk after next; then wait for this chunk's (every chunk is requested and
+                    // awaited, also one that lies outside the matrix: the TMA unit zero-fills it)
+                    if (c < 2)
+                        request_aux(it, c + 2, tchunk + 2);
+                    else if (have_next)
+                        request_aux(nxt_it, c - 2, tchunk + 2);
+                    mbar_wait(my_aux_bar + (tchunk & 3), (tchunk >> 2) & 1, 5);
+                }
+                ++tchunk;
                 if (!(col0 < p.N && row0 < p.M)) return;  // (G = 2: the odd CTA's rows of the last tile may all lie beyond M)
                 float f[32];
                 if (add_bias) {
@@ -361,8 +399,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 } else {
                     // bf16 outputs: 32 rows x 64 B, chunk index XOR ((row >> 1) & 3) == TMA SWIZZLE_64B
                     uint32_t o[16], o2[16];
+                    uint32_t axs[16];
+                    if (AUX_TMA) {
+                        // this lane's row of the aux chunk: 64 B, 16-byte pieces XOR-swizzled like the output (SWIZZLE_64B)
+                        const uint32_t ra = smem_u32(abuf) + lane * 64;
+                        const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(axs[4 * j]), "=r"(axs[4 * j + 1]), "=r"(axs[4 * j + 2]), "=r"(axs[4 * j + 3])
+                                         : "r"(ra + ((j ^ sw) << 4))
+                                         : "memory");
+                    }
                     if (epi == VB_EPI_BF16_RESID) {
-                        const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+                        const uint32_t* ax = AUX_TMA ? axs : reinterpret_cast<const uint32_t*>(aux_cur);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float2 r = unpack_bf16x2(ax[j]);
@@ -376,7 +426,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             o[j] = pack_bf16x2(f[2 * j] * dgelu_erf(z.x), f[2 * j + 1] * dgelu_erf(z.y));
                         }
                     } else if (epi == VB_EPI_BF16_MULAUX) {
-                        const uint32_t* ax = reinterpret_cast<const uint32_t*>(aux_cur);
+                        const uint32_t* ax = AUX_TMA ? axs : reinterpret_cast<const uint32_t*>(aux_cur);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float2 g = unpack_bf16x2(ax[j]);
@@ -424,14 +474,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (col0 + lane < p.N) atomicAdd(p.out_colsum + col0 + lane, cs[0]);
                     }
                     uint8_t* b0;
-                    if (two) {
+                    if (AUX_TMA) {
+                        b0 = abuf;  // free: the store that last read it was awaited before the aux load was issued
+                        ++ring;
+                    } else if (two) {
                         b0 = stg + (ring % (NBUF / 2)) * 4096;
                         if (elect_one()) tma_store_wait_read<NBUF / 2 - 1>();
                     } else {
                         b0 = stg + (ring % NBUF) * 2048;
                         if (elect_one()) tma_store_wait_read<NBUF - 1>();
                     }
-                    ++ring;
+                    if (!AUX_TMA) ++ring;
                     __syncwarp();
                     const uint32_t rowaddr = smem_u32(b0) + lane * 64;
                     const uint32_t sw = (lane >> 1) & 3;
@@ -460,7 +513,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tmem_ld_32x32b_x32(tacc, va);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                if (c < 3) load_aux(aux_nxt, colbase + c * 32 + 32);
+                if (!AUX_TMA && c < 3) load_aux(aux_nxt, colbase + c * 32 + 32);
                 if ((c & 1) == 0) {
                     tmem_ld_wait_x32(va);
                     if (c < 3) tmem_ld_32x32b_x32(tacc + (c + 1) * 32, vb);
@@ -521,7 +574,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 template <int A_MN, int B_MN, int G, int EPI_T, int DEEP>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
-                       const GemmKernelParams& p, cudaStream_t stream) {
+                       const CUtensorMap& tmAux, const GemmKernelParams& p, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     VB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -546,7 +599,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = G > 1 ? 1 : 0;
-    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p));
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, tmAux, p));
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
@@ -656,6 +709,13 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
         }
     }
 
+    CUtensorMap tmAux = tmC;  // residual / saved-GELU' operand, read through TMA by the pair kernels of those epilogues
+    if (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_MULAUX) {
+        rc = make_tensor_map_2d(&tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->aux, a->n, a->m, a->ld_aux * 2, 32, 32,
+                                CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+    }
+
     GemmKernelParams p;
     p.M = a->m;
     p.N = a->n;
@@ -678,7 +738,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     p.out_colsum = a->out_colsum;
 
     // the hot combinations of the training step get an epilogue fixed at compile time, everything else the generic kernel
-#define VB_LAUNCH(AL, BL, GG, EP, DP) return launch_gemm<AL, BL, GG, EP, DP>(tmA, tmB, tmC, tmC2, p, stream)
+#define VB_LAUNCH(AL, BL, GG, EP, DP) return launch_gemm<AL, BL, GG, EP, DP>(tmA, tmB, tmC, tmC2, tmAux, p, stream)
 #define VB_LAUNCH_PAIR(AL, BL, EP, DP)                     \
     do {                                                   \
         if (deep_mode == 0) VB_LAUNCH(AL, BL, 2, EP, 0);   \
@@ -690,7 +750,12 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     if (G == 2) {
         if (al == 0 && bl == 0) {
             if (epi == VB_EPI_BF16) VB_LAUNCH_PAIR(0, 0, VB_EPI_BF16, 0);
-            if (epi == VB_EPI_BF16_RESID) VB_LAUNCH_PAIR(0, 0, VB_EPI_BF16_RESID, 0);
+            if (epi == VB_EPI_BF16_RESID) {
+                // short K (proj): the epilogue paces the tile, take the TMA-fed residual (5-stage ring); long K (fc2): the
+                // main loop does, keep the 6-stage ring
+                if (a->k >= 2048) VB_LAUNCH_PAIR(0, 0, VB_EPI_BF16_RESID, 0);
+                VB_LAUNCH_PAIR(0, 0, VB_EPI_BF16_RESID, 1);
+            }
             if (epi == VB_EPI_BF16_GELU_GRAD) VB_LAUNCH_PAIR(0, 0, VB_EPI_BF16_GELU_GRAD, 1);
             VB_LAUNCH(0, 0, 2, -1, 0);
         }

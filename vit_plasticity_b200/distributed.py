@@ -56,7 +56,7 @@ class ComputingManagerConfig:
     backend: str = "cpu:gloo,cuda:nccl"
     dp: int = 0
     tp: int = 1
-    bucket_mb: int = 64
+    bucket_mb: int = 256
 
     def __post_init__(self) -> None:
         if not self.dp:
@@ -66,7 +66,7 @@ class ComputingManagerConfig:
 class DataParallel(nn.Module):
     """Gradient-averaging wrapper; ``forward`` delegates to the wrapped module."""
 
-    def __init__(self, module: nn.Module, process_group=None, bucket_mb: int = 64):
+    def __init__(self, module: nn.Module, process_group=None, bucket_mb: int = 256, overlap: bool | None = None):
         super().__init__()
         self.module = module
         self.group = process_group
@@ -74,6 +74,14 @@ class DataParallel(nn.Module):
         params = [p for p in module.parameters() if p.requires_grad]
         if not params:
             raise ValueError("DataParallel: the module has no trainable parameter")
+        # overlap=True: one all-reduce per bucket, launched from the gradient hooks while backward still runs;
+        # overlap=False: ONE all-reduce of the whole arena after backward (NCCL's CTAs then never take SMs away from the
+        # persistent GEMM / attention kernels, which are sized to all 148 SMs). Environment overrides for measurement:
+        # VB_DP_OVERLAP=0/1, VB_DP_BUCKET_MB=<int>.
+        if overlap is None:
+            overlap = os.environ.get("VB_DP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap)
+        bucket_mb = int(os.environ.get("VB_DP_BUCKET_MB", bucket_mb))
         cap = max(1, int(bucket_mb * 1024 * 1024 // 4))
         # One flat fp32 arena holds every trainable gradient (slots 16-byte aligned, in reverse registration order: the
         # order backward produces them); the buckets are consecutive slices of it. finetune.FusedSGD steps straight from
@@ -101,6 +109,10 @@ class DataParallel(nn.Module):
             n_in_bucket += 1
         self.buckets.append(self.arena[b_start:off])
         self._expected.append(n_in_bucket)
+        self._used = off
+        # the mean is taken by NCCL (ncclAvg) where the backend has it; gloo (the CPU tests) sums and divides afterwards
+        backend = dist.get_backend(process_group) if dist.is_initialized() else "none"
+        self._op = dist.ReduceOp.AVG if backend == "nccl" else dist.ReduceOp.SUM
         self._ready = [0] * len(self.buckets)
         self._seen: set = set()
         self._handles: list = []
@@ -142,13 +154,13 @@ class DataParallel(nn.Module):
             return
         self._seen.add(p)
         self._ready[b] += 1
-        if self._ready[b] == self._expected[b] and not self._launched[b]:
+        if self.overlap and self._ready[b] == self._expected[b] and not self._launched[b]:
             self._launch(b)
 
     def _launch(self, b: int) -> None:
         self._launched[b] = True
         if self.world > 1:
-            self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._handles.append(dist.all_reduce(self.buckets[b], op=self._op, group=self.group, async_op=True))
 
     def finish_grad_sync(self) -> None:
         """Call after the last backward of a step: flushes incomplete buckets (parameters that received no gradient
@@ -159,12 +171,15 @@ class DataParallel(nn.Module):
             if p.grad is None:
                 slot.zero_()
                 p.grad = slot
+        if not self.overlap and self.world > 1 and not any(self._launched):
+            self._launched = [True] * len(self.buckets)
+            self._handles.append(dist.all_reduce(self.arena[: self._used], op=self._op, group=self.group, async_op=True))
         for b in range(len(self.buckets)):
             if not self._launched[b]:
                 self._launch(b)
         for h in self._handles:
             h.wait()
-        if self.world > 1:
+        if self.world > 1 and self._op == dist.ReduceOp.SUM:
             for flat in self.buckets:
                 flat.div_(self.world)
         self._handles.clear()
