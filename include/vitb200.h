@@ -146,6 +146,21 @@ int vb_cast_bf16_to_f32(const void* src, float* dst, int64_t n, vb_stream_t stre
  * (subtracted in fp32). */
 int vb_im2col_patches(const float* img, const float* img2, void* patches, int32_t n, int32_t c, int32_t h,
                       int32_t w, int32_t p, vb_stream_t stream);
+/* Device-side input pipeline: the reference's PIL / torchvision preprocessing of uint8 images (data/images/utils.py:337-366:
+ * Resize -> CenterCrop -> ToTensor -> Normalize for eval / analysis / probing; RandomResizedCrop -> RandomHorizontalFlip ->
+ * ToTensor -> Normalize for training), bit for bit: Pillow's two-pass 8-bit bilinear ImagingResample with the 22-bit fixed-point
+ * tap tables the host precomputes, then the 3 x 256 table lut[c][v] = fp32((fp32(v) / 255 - mean[c]) / std[c]).
+ *   src        uint8 [n, src_h, src_w, 3] (HWC)
+ *   params     int32 [n, 8] = {top, left, crop_h, crop_w, flip, row_table, col_table, 0} per image, or NULL (whole image, table 0)
+ *   tab_bounds int32 [n_tables, out, 2] = (first source index, tap count);  tab_coef int32 [n_tables, out, ksize]
+ *   max_src_rows_per_strip: the largest number of source rows any strip of output rows needs (strip = patch rows when
+ *              out_patches is given, else 16), sizes the shared-memory intermediate
+ *   out_f32    f32 [n, 3, out, out] or NULL;  out_patches bf16 [n * (out/patch)^2, 3 * patch * patch] or NULL (same layout
+ *              as vb_im2col_patches) */
+int vb_preprocess_u8(const uint8_t* src, int32_t n, int32_t src_h, int32_t src_w, const int32_t* params,
+                     const int32_t* tab_bounds, const int32_t* tab_coef, int32_t n_tables, int32_t ksize,
+                     int32_t max_src_rows_per_strip, const float* lut, int32_t out, float* out_f32, void* out_patches,
+                     int32_t patch, vb_stream_t stream);
 /* tokens[b, 0, :] = cls + pos[0]; tokens[b, 1+i, :] = patch_out[b*np + i, :] + pos[1+i]
  * (architecture.py:666-675). patch_out bf16 [batch*np, E] -> tokens bf16 [batch*(np+1), E];
  * tokens_f32 (optional, may be NULL) receives the same values before the bf16 rounding. */

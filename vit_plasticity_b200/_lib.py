@@ -66,6 +66,10 @@ SIGNATURES = {
     "vb_launch_count": (c_int64, []),
     "vb_reset_launch_count": (None, []),
     "vb_gemm_bf16": (c_int32, [POINTER(GemmArgs), c_void_p]),
+    "vb_preprocess_u8": (
+        c_int32,
+        [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p],
+    ),
     "vb_set_gemm_cta_pair": (None, [c_int32]),
     "vb_get_gemm_cta_pair": (c_int32, []),
     "vb_layernorm_fwd": (
@@ -339,6 +343,28 @@ def im2col_patches(img: torch.Tensor, p: int, img2: torch.Tensor | None = None) 
     patches = torch.empty(n * (h // p) * (w // p), c * p * p, device=img.device, dtype=torch.bfloat16)
     _check(lib().vb_im2col_patches(img.data_ptr(), _ptr(img2), patches.data_ptr(), n, c, h, w, p, _stream()), "vb_im2col_patches")
     return patches
+
+
+def preprocess_u8(src, params, tab_bounds, tab_coef, max_src_rows, lut, out, *, want_f32=True, patch=0):
+    """uint8 [n, h, w, 3] -> (f32 [n, 3, out, out] | None, bf16 patch rows | None); see ``vb_preprocess_u8``."""
+    _req(src, torch.uint8, "src")
+    assert src.dim() == 4 and src.shape[3] == 3 and src.is_contiguous()
+    for t, name in ((tab_bounds, "tab_bounds"), (tab_coef, "tab_coef")):
+        _req(t, torch.int32, name)
+    _req(lut, torch.float32, "lut")
+    if params is not None:
+        _req(params, torch.int32, "params")
+        assert params.shape == (src.shape[0], 8) and params.is_contiguous()
+    n, h, w, _ = src.shape
+    n_tables, out_t, ksize = tab_coef.shape
+    assert out_t == out and tab_bounds.shape == (n_tables, out, 2)
+    img = torch.empty(n, 3, out, out, device=src.device, dtype=torch.float32) if want_f32 else None
+    patches = torch.empty(n * (out // patch) ** 2, 3 * patch * patch, device=src.device, dtype=torch.bfloat16) if patch else None
+    _check(
+        lib().vb_preprocess_u8(src.data_ptr(), n, h, w, _ptr(params), tab_bounds.data_ptr(), tab_coef.data_ptr(), n_tables, ksize, max_src_rows, lut.data_ptr(), out, _ptr(img), _ptr(patches), patch, _stream()),
+        "vb_preprocess_u8",
+    )
+    return img, patches
 
 
 def assemble_tokens(patch_out, patch_out_f32, cls, pos, batch, np_, e, *, want_bf16=True, want_f32=False):

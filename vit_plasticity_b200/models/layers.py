@@ -254,6 +254,10 @@ class Embedding(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         _require_cuda(x, "Embedding")
         conv = self.patching.patching[0]
+        if x.dim() == 2 and x.dtype == torch.bfloat16:
+            # bf16 patch rows [N * n_patches, C*P*P] straight from the device-side input pipeline
+            # (preprocess.DevicePreprocessor.patches): the im2col pass and the fp32 image are skipped
+            return ops.EmbedFn.apply(x, conv.weight, conv.bias, self.cls_token, self.pos_emb, self.patching.patch_size)
         if x.dtype != torch.float32:
             x = x.float()
         return ops.EmbedFn.apply(x, conv.weight, conv.bias, self.cls_token, self.pos_emb, self.patching.patch_size)

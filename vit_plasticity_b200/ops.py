@@ -437,12 +437,17 @@ class EmbedFn(Function):
 
     @staticmethod
     def forward(ctx, img, conv_w, conv_b, cls, pos, patch):
-        n = img.shape[0]
         e = conv_w.shape[0]
-        patches = L.im2col_patches(img.contiguous(), patch)
+        if img.dim() == 2:  # already bf16 patch rows (device-side input pipeline): n_patches rows per image
+            patches = img.contiguous()
+            np_ = pos.shape[-2] - 1
+            n = patches.shape[0] // np_
+        else:
+            n = img.shape[0]
+            patches = L.im2col_patches(img.contiguous(), patch)
+            np_ = patches.shape[0] // n
         w16 = shadow_bf16(conv_w)  # [E, C*P*P]: K index = c*P*P + py*P + px, the Conv2d weight layout
         po = linear_fwd(patches, w16, _f32c(conv_b))
-        np_ = patches.shape[0] // n
         clsf, posf = _f32c(cls).reshape(-1), _f32c(pos).reshape(np_ + 1, e)
         tokens, _ = L.assemble_tokens(po, None, clsf, posf, n, np_, e)
         ctx.save_for_backward(patches)
