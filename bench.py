@@ -90,7 +90,7 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, 0.0
 
     def start(self):
         try:
@@ -102,20 +102,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """The timed region starts now (nvidia-smi itself is started earlier: it can take over a second to come up)."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        timed_rows = [r for t, r in self.rows if t >= self.t_mark]
+        window = "timed region"
+        if not timed_rows:  # sampler slower than the timed region: fall back to the warm-up steps (same load)
+            timed_rows, window = [r for _, r in self.rows], "warm-up + timed region"
+        self.rows = timed_rows
         sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
         mx = [int(float(r[1])) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         # the upper half of the samples is "under load" (idle gaps between host phases pull the plain median down)
         load = sm[len(sm) // 2 :] if sm else []
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -247,15 +256,17 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # ---- warm-up (untimed) ----
     for i in range(max(3, args.warmup)):
         step_resident(i)
     torch.cuda.synchronize()
 
     # ---- timed: inputs resident in HBM; GEMM launches individually event-timed for the roofline ----
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     _lib.reset_launch_count()
     _lib.GEMM_EVENTS = []
     ms_total = timed(step_resident, args.steps)
@@ -277,6 +288,41 @@ def main():
         h2d = B * 3 * 224 * 224 * 4 + B * 8
         e2e = {"value": round(world * B * args.steps / (ms_e2e / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                "ms_per_step": round(ms_e2e / args.steps, 3)}
+
+    # ---- secondary: the same step fed by the device-side input pipeline: the batch crosses PCIe as
+    # uint8 32x32x3 CIFAR-shaped images; RandomResizedCrop / flip / ToTensor / Normalize (the reference's "train"
+    # transform, bit-exact against PIL / torchvision) run on the GPU and emit the patch-embed GEMM's bf16 operand ----
+    pipe = None
+    if not args.no_e2e:
+        from vit_plasticity_b200.preprocess import DevicePreprocessor
+
+        pre = DevicePreprocessor(224, "train", dev)
+        hu8 = [torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_host)]
+
+        ustaged = {}
+
+        def u_prep(i):
+            # host side of the next batch (crop boxes / flips in torchvision's draw order, 1.5 MB uint8 copy) while the
+            # GPU is busy with the current step
+            ustaged[i] = (hu8[i % n_host].to(dev, non_blocking=True), pre.make_params(B, 32, 32))
+
+        def step_u8(i, last=False):
+            if i not in ustaged:
+                u_prep(i)
+            xu8, params = ustaged.pop(i)
+            x = pre.patches(xu8, params)
+            loss, _ = train_step(dp or model, opt, [(x, devb[i % n_host][1])], grad_clip=1.0, after_backward=after)
+            if not last:
+                u_prep(i + 1)
+            return float(loss)
+
+        for i in range(2):
+            step_u8(i, last=(i == 1))
+        ustaged.clear()
+        ms_u8 = timed(lambda i: step_u8(i, last=(i == args.steps - 1)), args.steps)
+        pipe = {"value": round(world * B * args.steps / (ms_u8 / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": (B * 32 * 32 * 3 + B * 32) * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": round(ms_u8 / args.steps, 3),
+                "source": "uint8 32x32x3 batch in pinned host memory; crop boxes / flips drawn on the host in torchvision's RNG order"}
 
     # ---- secondary: plasticity estimator pairs/s (each rank takes its own shard of pairs; no collective) ----
     plast = None
@@ -348,7 +394,7 @@ def main():
                      "kernel": "gemm_tcgen05_kernel (all fwd/dgrad/wgrad launches of the timed steps, CUDA events per launch)", "peak_source": pk["source"] + " bf16_tflops_sustained",
                      "gemm_share_of_step": round(gemm_ms / ms_total, 4), "gemm_launches": len(gemm_events),
                      "whole_step_frac": round(step_flops * args.steps / (ms_total / 1e3) / 1e12 / pk["bf16_tflops_sustained"], 4) if step_flops else None},
-        "cpu_baseline": cpu, "clocks": clocks, "plasticity": plast,
+        "cpu_baseline": cpu, "clocks": clocks, "plasticity": plast, "e2e_u8_input_pipeline": pipe,
     }
     print(json.dumps(out))
     if world > 1:
