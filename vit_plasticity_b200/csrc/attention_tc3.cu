@@ -780,6 +780,373 @@ attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
 #undef VB_STAMP
 }
 
+// =====================================================================================================
+// backward, key-domain schedule ("kd"): S and dP are computed ONCE per (key tile, query chunk), keys on the TMEM lanes
+// =====================================================================================================
+// Per item: key tiles j = 0, 1 (keys [128 j, 128 j + 128)), query chunks c = 0..3 (64, 64, 64, 16 queries). Chunk (j, c):
+//   MMA1   S^T = K_j Q_c^T, dP^T = V_j dO_c^T                       (SS, N = 64 / 16)        -> chunk buffer (2 of them)
+//   math   P^T = exp2(S^T c - lse_q), dS^T = P^T (dP^T - delta_q) / 8, packed bf16 over the fp32 values in TMEM (A operands
+//          of MMA2) and dS^T ALSO to shared memory as an MN-major A operand [key][query] (block = two query chunks)
+//   MMA2   dV_j += P^T dO_c, dK_j += dS^T Q_c                       (TS)
+//   MMA3   after the odd chunk of a block: dQ_block += dS_block K_j  (SS, M = 128 queries, K = the tile's 128 / 80 keys)
+// Against the two-domain kernel above this halves the score-shaped MMAs, the exponentials and the TMEM traffic; dQ stays in
+// TMEM across both key tiles, dV_j / dK_j are drained after each tile by the drain warpgroup.
+// TMEM: chunk buffers [0,128) [128,256) (S^T at +0, dP^T at +64), dV [256,320), dK [320,384), dQ block 0 [384,448), 1 [448,512).
+// Shared memory: K, V single-buffered but reloaded per key tile (tile 0 of the next item loads while tile 1 computes);
+// Q, dO double-buffered per item; two 32 KB dS^T blocks; lse / delta per item stage.
+constexpr int KD_KV_BYTES = 2 * OPER_BYTES;                 // K, V
+constexpr int KD_QDO_BYTES = 2 * OPER_BYTES;                // Q, dO (per stage)
+constexpr int KD_DS_BLOCK = 2 * 128 * 128;                  // two 64-query MN chunks of [128 keys][128 B]
+constexpr int KD_OFF_QDO = KD_KV_BYTES;
+constexpr int KD_OFF_DS = KD_OFF_QDO + 2 * KD_QDO_BYTES;
+constexpr int KD_OFF_TAIL = KD_OFF_DS + 2 * KD_DS_BLOCK;
+constexpr int KD_SMEM = KD_OFF_TAIL + 4096 + 512 + 1024;    // + lse / delta + barriers + alignment slack
+static_assert(KD_SMEM <= 232448, "shared memory budget");
+constexpr uint32_t KD_COL_DV = 256, KD_COL_DK = 320, KD_COL_DQ = 384;
+constexpr int KD_THREADS = 24 * 32;
+
+__global__ void __launch_bounds__(KD_THREADS, 1)
+attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                        const __grid_constant__ CUtensorMap tmKV0, const __grid_constant__ CUtensorMap tmKV1,
+                        const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
+                        float* __restrict__ dbias, int L, int H, int n_items) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align_smem(smem_raw);
+    float* sL = reinterpret_cast<float*>(smem + KD_OFF_TAIL);  // [2][256] lse * log2(e); +inf for q >= L
+    float* sD = sL + 512;                                      // [2][256] delta / 8;     0 for q >= L
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 512);
+    uint64_t *qdo_full = bars, *qdo_empty = bars + 2, *kv_full = bars + 4, *kv_empty = bars + 6, *s_ready = bars + 8,
+             *p_ready = bars + 10, *c_free = bars + 12, *ds_free = bars + 14, *kv_acc_ready = bars + 16, *kv_acc_free = bars + 17,
+             *q_acc_ready = bars + 18, *q_acc_free = bars + 19;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int E = H * HD;
+    const int64_t ld3 = 3 * (int64_t)E;
+    const int n_local = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int G = 8 * n_local;  // chunks: 2 key tiles x 4 query chunks per item
+
+    if (warp == B_WARP_TMA && elect_one()) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmDO);
+        tma_prefetch_desc(&tmKV0);
+        tma_prefetch_desc(&tmKV1);
+    }
+    if (warp == B_WARP_MMA1) {
+        if (elect_one()) {
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&qdo_full[i], 2);  // TMA bytes + the producer warp's lse / delta staging
+                mbar_init(&qdo_empty[i], 1);
+                mbar_init(&kv_full[i], 1);   // [tile]
+                mbar_init(&kv_empty[i], 1);
+                mbar_init(&s_ready[i], 1);
+                mbar_init(&p_ready[i], GROUP_WARPS);
+                mbar_init(&c_free[i], 1);
+                mbar_init(&ds_free[i], 1);   // [block]
+            }
+            mbar_init(kv_acc_ready, 1);
+            mbar_init(kv_acc_free, DRAIN_WARPS);
+            mbar_init(q_acc_ready, 1);
+            mbar_init(q_acc_free, DRAIN_WARPS);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t smem_lo = smem_u32(smem) >> 4;
+    constexpr uint32_t A_K = 0, A_V = OPER_BYTES >> 4;  // 16-byte units
+    constexpr uint32_t TILE16 = TILE_BYTES >> 4;
+
+    if (warp >= B_WARP_DRAIN0) {
+        // =========================== drain: dV_j, dK_j after every key tile, dQ after the item ===========================
+        setmaxnreg_inc<96>();
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint32_t a[32], a2[32];
+        auto load64 = [&](uint32_t col) {
+            tmem_ld_32x32b_x32(lane_addr + col, a);
+            tmem_ld_32x32b_x32(lane_addr + col + 32, a2);
+            tmem_ld_wait();
+            reg_fence(a);
+            reg_fence(a2);
+        };
+        auto release = [&](uint64_t* bar) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        };
+        auto put = [&](bool ok, bf16* dst, float* dcol) {
+            if (ok) {
+                store_32cols_bf16(dst, a, 1.f);
+                store_32cols_bf16(dst + 32, a2, 1.f);
+            }
+            if (dbias != nullptr) {
+                warp_colsum32_atomic(a, ok, dcol, lane);
+                warp_colsum32_atomic(a2, ok, dcol + 32, lane);
+            }
+        };
+        for (int n = 0; n < n_local; ++n) {
+            const int it = blockIdx.x + n * gridDim.x;
+            const int b = it / H, hd = it - b * H;
+            bf16* dbase = dqkv + (int64_t)b * L * ld3 + hd * HD;
+            for (int j = 0; j < 2; ++j) {
+                const int t = 2 * n + j;
+                mbar_wait(kv_acc_ready, t & 1, 74);
+                tc_fence_after();
+                const int r = j * 128 + row;  // key
+                load64(KD_COL_DV);
+                put(r < L, dbase + (int64_t)r * ld3 + 2 * E, dbias + 2 * E + hd * HD);
+                load64(KD_COL_DK);
+                release(kv_acc_free);
+                put(r < L, dbase + (int64_t)r * ld3 + E, dbias + E + hd * HD);
+            }
+            mbar_wait(q_acc_ready, n & 1, 77);
+            tc_fence_after();
+            load64(KD_COL_DQ);
+            put(row < L, dbase + (int64_t)row * ld3, dbias + hd * HD);  // queries 0..127
+            load64(KD_COL_DQ + 64);
+            release(q_acc_free);
+            put(128 + row < L, dbase + (int64_t)(128 + row) * ld3, dbias + hd * HD);  // queries 128..255
+        }
+    } else if (warp >= B_WARP_TMA) {
+    setmaxnreg_dec<32>();
+    if (warp == B_WARP_TMA) {
+        // =========================== TMA producer (+ lse / delta staging) ===========================
+        for (int n = 0; n < n_local; ++n) {
+            const int it = blockIdx.x + n * gridDim.x;
+            const int b = it / H, hd = it - b * H;
+            const int s = n & 1;
+            // K, V of key tile 0 (free once tile 0 of the previous item is done: that is half an item ago)
+            mbar_wait(&kv_empty[0], (n & 1) ^ 1, 70);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&kv_full[0], 2 * TILE_BYTES);
+                tma_load_3d(smem, &tmKV0, &kv_full[0], E + hd * HD, 0, b);
+                tma_load_3d(smem + OPER_BYTES, &tmKV0, &kv_full[0], 2 * E + hd * HD, 0, b);
+            }
+            __syncwarp();
+            // Q, dO of the item (double-buffered)
+            mbar_wait(&qdo_empty[s], ((n >> 1) & 1) ^ 1, 71);
+            if (elect_one()) {
+                uint8_t* st = smem + KD_OFF_QDO + s * KD_QDO_BYTES;
+                mbar_arrive_expect_tx(&qdo_full[s], KD_QDO_BYTES);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int r0 = h2 * BOX_ROWS;
+                    tma_load_3d(st + r0 * 128, &tmQKV, &qdo_full[s], hd * HD, r0, b);
+                    tma_load_3d(st + OPER_BYTES + r0 * 128, &tmDO, &qdo_full[s], hd * HD, r0, b);
+                }
+            }
+            __syncwarp();
+            float lv[8], dv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = lane + 32 * i;
+                lv[i] = q < L ? __ldg(lse + (int64_t)it * L + q) : INFINITY;
+                dv[i] = q < L ? __ldg(delta + (int64_t)it * L + q) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sL[s * 256 + lane + 32 * i] = lv[i] * LOG2E;
+                sD[s * 256 + lane + 32 * i] = dv[i] * 0.125f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qdo_full[s]);
+            // K, V of key tile 1 (rows 128..207; free once tile 1 of the previous item is done)
+            mbar_wait(&kv_empty[1], (n & 1) ^ 1, 72);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&kv_full[1], 2 * (ROWS - 128) * 128);
+                tma_load_3d(smem + TILE_BYTES, &tmKV1, &kv_full[1], E + hd * HD, 128, b);
+                tma_load_3d(smem + OPER_BYTES + TILE_BYTES, &tmKV1, &kv_full[1], 2 * E + hd * HD, 128, b);
+            }
+            __syncwarp();
+        }
+    } else if (warp == B_WARP_MMA1) {
+        // =========================== MMA1 issuer: S^T, dP^T of chunk g into buffer g & 1 ===========================
+        const uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0), idesc16 = make_idesc_bf16(128, 16, 0, 0);
+        for (int g = 0; g < G; ++g) {
+            const int n = g >> 3, j = (g >> 2) & 1, c = g & 3, s = n & 1, cb = g & 1;
+            if ((g & 7) == 0) mbar_wait(&qdo_full[s], (n >> 1) & 1, 73);
+            if (c == 0) mbar_wait(&kv_full[j], n & 1, 78);
+            mbar_wait(&c_free[cb], ((g >> 1) & 1) ^ 1, 79);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t qdo = smem_lo + ((KD_OFF_QDO + s * KD_QDO_BYTES) >> 4);
+                const uint32_t crow = c * 64 * 8;  // chunk queries = operand rows [64 c, ...)
+                const uint32_t a1 = smem_lo + A_K + j * TILE16, a2 = smem_lo + A_V + j * TILE16;
+                const uint32_t b1 = qdo + crow, b2 = qdo + (OPER_BYTES >> 4) + crow;
+                const uint32_t idesc = c == 3 ? idesc16 : idesc64;
+                const uint32_t d = tmem_base + cb * 128;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(d, make_desc((a1 | LBO_K) + 2 * k, DESC_HI), make_desc((b1 | LBO_K) + 2 * k, DESC_HI), idesc, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(d + 64, make_desc((a2 | LBO_K) + 2 * k, DESC_HI), make_desc((b2 | LBO_K) + 2 * k, DESC_HI), idesc, k > 0);
+                umma_commit(&s_ready[cb]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == B_WARP_MMA2) {
+        // =========================== MMA2 / MMA3 issuer ===========================
+        const uint32_t idesc2 = make_idesc_bf16(128, HD, 0, 1);  // A from TMEM (K-major), B MN-major
+        const uint32_t idesc3 = make_idesc_bf16(128, HD, 1, 1);  // A = dS^T block in smem, MN-major; B = K_j MN-major
+        constexpr uint32_t LBO_DS = (16384u >> 4) << 16;          // the two 64-query chunks of a block are 16 KB apart
+        for (int g = 0; g < G; ++g) {
+            const int n = g >> 3, j = (g >> 2) & 1, c = g & 3, s = n & 1, cb = g & 1;
+            const int t = 2 * n + j;
+            mbar_wait(&p_ready[cb], (g >> 1) & 1, 72);
+            if (c == 0) mbar_wait(kv_acc_free, (t & 1) ^ 1, 73);           // dV / dK of the previous key tile read out
+            if (j == 0 && c == 1) mbar_wait(q_acc_free, (n & 1) ^ 1, 80);  // dQ of the previous item read out
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t qdo = smem_lo + ((KD_OFF_QDO + s * KD_QDO_BYTES) >> 4);
+                const uint32_t crow = c * 64 * 8;
+                const int ksteps = c == 3 ? 1 : 4;  // 16 queries per k-step
+                const uint32_t pbuf = tmem_base + cb * 128;
+                const uint32_t domn = (qdo + (OPER_BYTES >> 4) + crow) | LBO_MN, qmn = (qdo + crow) | LBO_MN;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < ksteps) {
+                        const uint32_t acol = (k >> 1) * 32 + (k & 1) * 8;
+                        umma_bf16_ts(tmem_base + KD_COL_DV, pbuf + acol, make_desc(domn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));       // dV_j += P^T dO_c
+                        umma_bf16_ts(tmem_base + KD_COL_DK, pbuf + 64 + acol, make_desc(qmn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));  // dK_j += dS^T Q_c
+                    }
+                umma_commit(&c_free[cb]);
+                if (c & 1) {
+                    // dQ_block += dS_block K_j over the tile's keys (tile 1 holds 80 staged keys: rows 208.. are not K)
+                    const int blk = c >> 1;
+                    const int kk = j == 0 ? 8 : (ROWS - 128) / 16;
+                    const uint32_t ds = (smem_lo + ((KD_OFF_DS + blk * KD_DS_BLOCK) >> 4)) | LBO_DS;
+                    const uint32_t kmn = (smem_lo + A_K + j * TILE16) | LBO_MN;
+                    for (int k = 0; k < kk; ++k)
+                        umma_bf16_ss(tmem_base + KD_COL_DQ + blk * 64, make_desc(ds + k * 128, DESC_HI), make_desc(kmn + k * 128, DESC_HI), idesc3,
+                                     (j > 0 || k > 0));
+                    umma_commit(&ds_free[blk]);
+                }
+                if (c == 3) {
+                    umma_commit(kv_acc_ready);
+                    umma_commit(&kv_empty[j]);  // K_j, V_j may be overwritten by the next item's tile
+                    if (j == 1) {
+                        umma_commit(q_acc_ready);
+                        umma_commit(&qdo_empty[s]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    } else {
+        // =========================== math warps: group 0 takes even chunks, group 1 odd chunks ===========================
+        setmaxnreg_inc<88>();
+        const int grp = warp >> 3;
+        const int quarter = warp & 3, hf = (warp >> 2) & 1;
+        const int row = quarter * 32 + lane;  // key within the tile
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const float c = 0.125f * LOG2E;
+        const int c0 = hf * 32;
+        const uint32_t ds_row = smem_u32(smem + KD_OFF_DS) + row * 128;  // this key's 128-byte row inside a 64-query chunk
+        const uint32_t sw = row & 7;
+
+        for (int g = grp; g < G; g += 2) {
+            const int n = g >> 3, j = (g >> 2) & 1, cc = g & 3, s = n & 1, cb = g & 1;
+            const float* sLs = sL + s * 256;
+            const float* sDs = sD + s * 256;
+            if ((g & 7) == grp) mbar_wait(&qdo_full[s], (n >> 1) & 1, 76);  // lse / delta of the item staged
+            // the dS^T block this chunk writes into must have been consumed by MMA3 of the previous key tile
+            mbar_wait(&ds_free[cc >> 1], ((2 * n + j) & 1) ^ 1, 81);
+            mbar_wait(&s_ready[cb], (g >> 1) & 1, 75);
+            tc_fence_after();
+            const uint32_t sbuf = lane_addr + cb * 128, dbuf = sbuf + 64;
+            const uint32_t ds_chunk = ds_row + (cc >> 1) * KD_DS_BLOCK + (cc & 1) * 16384;
+            if (cc < 3) {
+                uint32_t sv[32], dv[32];
+                tmem_ld_32x32b_x32(sbuf + c0, sv);
+                tmem_ld_32x32b_x32(dbuf + c0, dv);
+                tmem_ld_wait();
+                reg_fence(sv);
+                reg_fence(dv);
+                uint32_t pp[16], pd[16];
+                const float* lq = sLs + cc * 64 + c0;  // same address for the whole warp: smem broadcast
+                const float* dq = sDs + cc * 64 + c0;
+#pragma unroll
+                for (int gq = 0; gq < 8; ++gq) {
+                    const float4 l4 = lds128(lq + 4 * gq), d4 = lds128(dq + 4 * gq);
+                    const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+                    float p[4], ds[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        p[i] = fast_ex2(fmaf(__uint_as_float(sv[4 * gq + i]), c, -lv[i]));
+                        ds[i] = p[i] * fmaf(__uint_as_float(dv[4 * gq + i]), 0.125f, -dl[i]);
+                    }
+                    pp[2 * gq] = pack_bf16x2(p[0], p[1]);
+                    pp[2 * gq + 1] = pack_bf16x2(p[2], p[3]);
+                    pd[2 * gq] = pack_bf16x2(ds[0], ds[1]);
+                    pd[2 * gq + 1] = pack_bf16x2(ds[2], ds[3]);
+                }
+                tmem_st_x16(sbuf + c0, pp);
+                tmem_st_x16(dbuf + c0, pd);
+                // dS^T also as the A operand of the dQ MMA: 32 queries = 64 bytes = pieces 4 hf .. 4 hf + 3 of this key's row
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_chunk + (((4 * hf + i) ^ sw) << 4)), "r"(pd[4 * i]),
+                                 "r"(pd[4 * i + 1]), "r"(pd[4 * i + 2]), "r"(pd[4 * i + 3])
+                                 : "memory");
+            } else if (hf == 0) {
+                // 16-query tail chunk (queries 192..207)
+                uint32_t sv[16], dv[16];
+                tmem_ld_32x32b_x16(sbuf, sv);
+                tmem_ld_32x32b_x16(dbuf, dv);
+                tmem_ld_wait();
+                reg_fence(sv);
+                reg_fence(dv);
+                uint32_t pp[8], pd[8];
+                const float* lq = sLs + 192;
+                const float* dq = sDs + 192;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    const float4 l4 = lds128(lq + 4 * gq), d4 = lds128(dq + 4 * gq);
+                    const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+                    float p[4], ds[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        p[i] = fast_ex2(fmaf(__uint_as_float(sv[4 * gq + i]), c, -lv[i]));
+                        ds[i] = p[i] * fmaf(__uint_as_float(dv[4 * gq + i]), 0.125f, -dl[i]);
+                    }
+                    pp[2 * gq] = pack_bf16x2(p[0], p[1]);
+                    pp[2 * gq + 1] = pack_bf16x2(p[2], p[3]);
+                    pd[2 * gq] = pack_bf16x2(ds[0], ds[1]);
+                    pd[2 * gq + 1] = pack_bf16x2(ds[2], ds[3]);
+                }
+                tmem_st_x8(sbuf, pp);
+                tmem_st_x8(dbuf, pd);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_chunk + ((i ^ sw) << 4)), "r"(pd[4 * i]),
+                                 "r"(pd[4 * i + 1]), "r"(pd[4 * i + 2]), "r"(pd[4 * i + 3])
+                                 : "memory");
+            }
+            tmem_st_wait();
+            fence_proxy_async_smem();  // the dS^T rows must be visible to the tensor core's shared-memory reads
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[cb]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == B_WARP_MMA1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 template <typename K>
 static int set_smem(K kern, int bytes, bool& done) {
     if (!done) {
@@ -869,7 +1236,28 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
         cudaFree(dbg);
         return VB_OK;
     }
-    attention_bwd_persistent_kernel<<<grid, B_THREADS, B_SMEM, stream>>>(tmQKV, tmDO, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
+    static const bool two_domain = []() {
+        const char* e = getenv("VITB200_ATTN_BWD");
+        return e != nullptr && e[0] == 'o';  // "old": the two-domain kernel (measurement / bisection)
+    }();
+    if (two_domain) {
+        attention_bwd_persistent_kernel<<<grid, B_THREADS, B_SMEM, stream>>>(tmQKV, tmDO, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
+        VB_CHECK_LAUNCH();
+        return VB_OK;
+    }
+    // key-domain kernel: K / V come in per key tile (128 and 80 rows), so they get their own boxes
+    CUtensorMap tmKV0, tmKV1;
+    const int64_t E = (int64_t)H * HD;
+    rc = make_tensor_map_3d(&tmKV0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, 3 * E, L, batch, 3 * E * 2, (uint64_t)L * 3 * E * 2, 64, 128, 1,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tensor_map_3d(&tmKV1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, 3 * E, L, batch, 3 * E * 2, (uint64_t)L * 3 * E * 2, 64, ROWS - 128, 1,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    static bool done_kd = false;
+    rc = set_smem(attention_bwd_kd_kernel, KD_SMEM, done_kd);
+    if (rc) return rc;
+    attention_bwd_kd_kernel<<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
