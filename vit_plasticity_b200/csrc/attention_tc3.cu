@@ -809,7 +809,11 @@ __global__ void __launch_bounds__(KD_THREADS, 1)
 attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const __grid_constant__ CUtensorMap tmKV0, const __grid_constant__ CUtensorMap tmKV1,
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
-                        float* __restrict__ dbias, int L, int H, int n_items) {
+                        float* __restrict__ dbias, int L, int H, int n_items, long long* __restrict__ dbg) {
+#define KD_STAMP(g, slot)                                                                                   \
+    do {                                                                                                    \
+        if (dbg != nullptr && blockIdx.x == 0 && (g) >= 16 && (g) < 80) dbg[((g)-16) * 16 + (slot)] = clock64(); \
+    } while (0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     float* sL = reinterpret_cast<float*>(smem + KD_OFF_TAIL);  // [2][256] lse * log2(e); +inf for q >= L
@@ -974,7 +978,9 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             const int n = g >> 3, j = (g >> 2) & 1, c = g & 3, s = n & 1, cb = g & 1;
             if ((g & 7) == 0) mbar_wait(&qdo_full[s], (n >> 1) & 1, 73);
             if (c == 0) mbar_wait(&kv_full[j], n & 1, 78);
+            if (lane == 0) KD_STAMP(g, 3);
             mbar_wait(&c_free[cb], ((g >> 1) & 1) ^ 1, 79);
+            if (lane == 0) KD_STAMP(g, 4);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t qdo = smem_lo + ((KD_OFF_QDO + s * KD_QDO_BYTES) >> 4);
@@ -1001,9 +1007,12 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         for (int g = 0; g < G; ++g) {
             const int n = g >> 3, j = (g >> 2) & 1, c = g & 3, s = n & 1, cb = g & 1;
             const int t = 2 * n + j;
+            if (lane == 0) KD_STAMP(g, 0);
             mbar_wait(&p_ready[cb], (g >> 1) & 1, 72);
+            if (lane == 0) KD_STAMP(g, 1);
             if (c == 0) mbar_wait(kv_acc_free, (t & 1) ^ 1, 73);           // dV / dK of the previous key tile read out
             if (j == 0 && c == 1) mbar_wait(q_acc_free, (n & 1) ^ 1, 80);  // dQ of the previous item read out
+            if (lane == 0) KD_STAMP(g, 2);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t qdo = smem_lo + ((KD_OFF_QDO + s * KD_QDO_BYTES) >> 4);
@@ -1060,8 +1069,12 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             const float* sDs = sD + s * 256;
             if ((g & 7) == grp) mbar_wait(&qdo_full[s], (n >> 1) & 1, 76);  // lse / delta of the item staged
             // the dS^T block this chunk writes into must have been consumed by MMA3 of the previous key tile
+            const bool stp = (warp & 7) == 0 && lane == 0;
+            if (stp) KD_STAMP(g, 5);
             mbar_wait(&ds_free[cc >> 1], ((2 * n + j) & 1) ^ 1, 81);
+            if (stp) KD_STAMP(g, 6);
             mbar_wait(&s_ready[cb], (g >> 1) & 1, 75);
+            if (stp) KD_STAMP(g, 7);
             tc_fence_after();
             const uint32_t sbuf = lane_addr + cb * 128, dbuf = sbuf + 64;
             const uint32_t ds_chunk = ds_row + (cc >> 1) * KD_DS_BLOCK + (cc & 1) * 16384;
@@ -1072,6 +1085,7 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 tmem_ld_wait();
                 reg_fence(sv);
                 reg_fence(dv);
+                if (stp) KD_STAMP(g, 10);
                 uint32_t pp[16], pd[16];
                 const float* lq = sLs + cc * 64 + c0;  // same address for the whole warp: smem broadcast
                 const float* dq = sDs + cc * 64 + c0;
@@ -1090,6 +1104,7 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                     pd[2 * gq] = pack_bf16x2(ds[0], ds[1]);
                     pd[2 * gq + 1] = pack_bf16x2(ds[2], ds[3]);
                 }
+                if (stp) KD_STAMP(g, 11);
                 tmem_st_x16(sbuf + c0, pp);
                 tmem_st_x16(dbuf + c0, pd);
                 // dS^T also as the A operand of the dQ MMA: 32 queries = 64 bytes = pieces 4 hf .. 4 hf + 3 of this key's row
@@ -1132,11 +1147,13 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                                  "r"(pd[4 * i + 1]), "r"(pd[4 * i + 2]), "r"(pd[4 * i + 3])
                                  : "memory");
             }
+            if (stp) KD_STAMP(g, 8);
             tmem_st_wait();
             fence_proxy_async_smem();  // the dS^T rows must be visible to the tensor core's shared-memory reads
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[cb]);
+            if (stp) KD_STAMP(g, 9);
         }
     }
     tc_fence_before();
@@ -1220,7 +1237,11 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
     const int n_items = batch * H;
     const int grid = n_items < num_sms() ? n_items : num_sms();
     static const bool dbg_on = getenv("VITB200_DBG_TIMING") != nullptr;  // development only
-    if (dbg_on) {
+    static const bool two_domain = []() {
+        const char* e = getenv("VITB200_ATTN_BWD");
+        return e != nullptr && e[0] == 'o';  // "old": the two-domain kernel (measurement / bisection)
+    }();
+    if (dbg_on && two_domain) {
         long long* dbg = nullptr;
         VB_CHECK_CUDA(cudaMallocManaged(&dbg, 64 * 16 * sizeof(long long)));
         VB_CHECK_CUDA(cudaMemset(dbg, 0, 64 * 16 * sizeof(long long)));
@@ -1236,10 +1257,6 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
         cudaFree(dbg);
         return VB_OK;
     }
-    static const bool two_domain = []() {
-        const char* e = getenv("VITB200_ATTN_BWD");
-        return e != nullptr && e[0] == 'o';  // "old": the two-domain kernel (measurement / bisection)
-    }();
     if (two_domain) {
         attention_bwd_persistent_kernel<<<grid, B_THREADS, B_SMEM, stream>>>(tmQKV, tmDO, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
         VB_CHECK_LAUNCH();
@@ -1257,7 +1274,23 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
     static bool done_kd = false;
     rc = set_smem(attention_bwd_kd_kernel, KD_SMEM, done_kd);
     if (rc) return rc;
-    attention_bwd_kd_kernel<<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items);
+    if (dbg_on) {
+        long long* dbg = nullptr;
+        VB_CHECK_CUDA(cudaMallocManaged(&dbg, 64 * 16 * sizeof(long long)));
+        VB_CHECK_CUDA(cudaMemset(dbg, 0, 64 * 16 * sizeof(long long)));
+        attention_bwd_kd_kernel<<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, dbg);
+        VB_CHECK_CUDA(cudaStreamSynchronize(stream));
+        const long long t0 = dbg[0];
+        printf("[kd timing] g: mma2{waitP< waitP> accfree>} mma1{cfree< cfree>} math{start dsfree> Sready> stores> arrive> ld> math>}\n");
+        for (int g = 0; g < 64; ++g) {
+            printf("[kd timing] %3d:", g + 16);
+            for (int i = 0; i < 12; ++i) printf(" %7lld", dbg[g * 16 + i] ? dbg[g * 16 + i] - t0 : -1);
+            printf("\n");
+        }
+        cudaFree(dbg);
+        return VB_OK;
+    }
+    attention_bwd_kd_kernel<<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
