@@ -58,7 +58,12 @@ enum vb_epilogue {
     VB_EPI_SUMSQ = 6,      /* sumsq[row / rows_per_sample, col / cols_per_group] += acc^2 ; nothing stored  */
     VB_EPI_BF16_GELU_GRAD = 7, /* z = acc (+ bias); out = gelu_erf(z); out2 = gelu_erf'(z)  (training forward of fc1:
                                   the derivative is saved instead of z, so the backward epilogue is one multiply) */
-    VB_EPI_BF16_MULAUX = 8 /* out = acc * aux                                      aux: bf16 [M,N] (= gelu'(z))     */
+    VB_EPI_BF16_MULAUX = 8, /* out = acc * aux                                      aux: bf16 [M,N] (= gelu'(z))     */
+    VB_EPI_BF16_ROWDOT = 9  /* out = acc; sumsq[(row / rows_per_sample) * n_groups + col / 64][row % rows_per_sample] =
+                               sum over the 64-column group of bf16(out) * aux  (cols_per_group must be 64). With
+                               out = dO (proj dgrad) and aux = O this is the attention backward's delta[b, h, q], taken
+                               from the epilogue registers instead of a pass over dO and O. Plain stores: every (row, group)
+                               is written exactly once.                                                      */
 };
 
 typedef struct vb_gemm_args {
@@ -77,7 +82,8 @@ typedef struct vb_gemm_args {
     int64_t ld_out;
     void* out2;         /* bf16 [M,N], GELU (may be NULL: z not stored) and GELU_GRAD only */
     int64_t ld_out2;
-    float* sumsq;       /* f32 [n_samples, n_groups], SUMSQ only (accumulated into; caller zeroes) */
+    float* sumsq;       /* f32 [n_samples, n_groups], SUMSQ (accumulated into; caller zeroes); ROWDOT: f32 [n_samples, n_groups,
+                           rows_per_sample], overwritten */
     int32_t rows_per_sample;
     int32_t cols_per_group; /* multiple of 128 */
     int32_t n_groups;
@@ -125,6 +131,11 @@ int vb_attention_bwd(const void* qkv, const void* out, const void* dout, const f
  * from the accumulators while they are drained instead of by a second pass over dqkv. */
 int vb_attention_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias,
                           void* workspace, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
+/* Same with delta ALREADY in `workspace` (f32 [batch, heads, seq], e.g. from the VB_EPI_BF16_ROWDOT epilogue of the GEMM
+ * that produced dout): `out` is not read, no delta pass is launched. seq <= 208 only; dbias may be NULL. */
+int vb_attention_bwd_with_delta(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias,
+                                const void* workspace, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim,
+                                vb_stream_t stream);
 /* Paired attention for the plasticity estimator: runs the core on qkv_a and qkv_b (same shapes) and writes
  * delta = attn(qkv_a) - attn(qkv_b), subtracted in fp32 before the bf16 down-cast. */
 int vb_attention_pair_delta(const void* qkv_a, const void* qkv_b, int64_t ld_qkv, void* delta, int64_t ld_delta,

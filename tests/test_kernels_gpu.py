@@ -191,6 +191,26 @@ def test_gemm_dgrad_mn_major_b_with_dgelu():
     _report("dgrad_mulaux_colsum", cs, out.float().sum(0), atol=2e-3, rtol=1e-4)
 
 
+def test_gemm_dgrad_rowdot_is_attention_delta():
+    """ROWDOT epilogue: dx = dy W stored as bf16 AND per-(row, 64-column group) dot products of the stored dx with a second
+    operand, laid out [sample, group, row-in-sample] — the attention backward's delta when the operand is O."""
+    L = _lib()
+    batch, seq, heads = 3, 197, 12
+    tokens, e = batch * seq, heads * 64
+    dy = _rand(tokens, e, seed=1).bfloat16()
+    w = _rand(e, e, seed=2, scale=0.05).bfloat16()
+    o = _rand(tokens, e, seed=3).bfloat16()
+    dx = torch.empty(tokens, e, device=DEV, dtype=torch.bfloat16)
+    delta = torch.full((batch, heads, seq), float("nan"), device=DEV, dtype=torch.float32)
+    L.gemm(dy, w, m=tokens, n=e, k=e, b_layout=1, epilogue=L.EPI_BF16_ROWDOT, aux=o, out=dx, sumsq=delta, rows_per_sample=seq, cols_per_group=64, n_groups=heads)
+    torch.cuda.synchronize()
+    ref = dy.float() @ w.float()
+    _report("rowdot.dx", dx, ref, atol=3e-2, rtol=1e-2)
+    # delta is defined on the STORED (bf16) dx, like the stand-alone delta kernel that reads dO and O from memory
+    dref = (dx.float() * o.float()).view(batch, seq, heads, 64).sum(-1).permute(0, 2, 1)
+    _report("rowdot.delta", delta.reshape(batch * heads, seq), dref.reshape(batch * heads, seq), atol=2e-3, rtol=1e-4)
+
+
 @pytest.mark.parametrize("tokens,n_out,k_in,split_k", [(256, 128, 256, 1), (1000, 768, 768, 3), (197 * 8, 2304, 768, 4), (333, 136, 200, 2), (197 * 16, 768, 3072, 0)])
 def test_gemm_wgrad_mn_major_both_splitk(tokens, n_out, k_in, split_k):
     L = _lib()
@@ -309,6 +329,20 @@ def test_attention_fwd_bwd(batch, seq, heads):
     torch.cuda.synchronize()
     _report("attn_dqkv_with_bias", dqkv2, qf.grad, atol=3e-2, rtol=3e-2)
     _report("attn_dbias", dbias, qf.grad.sum(0), atol=5e-2, rtol=2e-2)
+
+
+def test_attention_bwd_with_precomputed_delta_matches():
+    """vb_attention_bwd_with_delta (delta supplied by the caller) == vb_attention_bwd (own delta pass), bit for bit."""
+    L = _lib()
+    batch, seq, heads = 4, 197, 12
+    qkv = _rand(batch * seq, 3 * heads * 64, seed=1).bfloat16()
+    out, lse = L.attention_fwd(qkv, batch, seq, heads, 64)
+    do = _rand(batch * seq, heads * 64, seed=2).bfloat16()
+    ref = L.attention_bwd(qkv, out, do, lse, batch, seq, heads, 64)
+    delta = (do.float() * out.float()).view(batch, seq, heads, 64).sum(-1).permute(0, 2, 1).contiguous()
+    got = L.attention_bwd(qkv, None, do, lse, batch, seq, heads, 64, delta=delta)
+    torch.cuda.synchronize()
+    _report("attn_bwd_with_delta", got, ref, atol=2e-3, rtol=2e-2)
 
 
 def test_attention_pair_delta():

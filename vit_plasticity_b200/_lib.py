@@ -27,6 +27,7 @@ EPI_F32_ADD = 5
 EPI_SUMSQ = 6
 EPI_BF16_GELU_GRAD = 7
 EPI_BF16_MULAUX = 8
+EPI_BF16_ROWDOT = 9
 
 
 class GemmArgs(Structure):
@@ -90,6 +91,10 @@ SIGNATURES = {
     "vb_attention_bwd_bias": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    ),
+    "vb_attention_bwd_with_delta": (
+        c_int32,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
     ),
     "vb_attention_pair_delta": (
         c_int32,
@@ -278,9 +283,21 @@ def attention_fwd(qkv, batch, seq, heads, head_dim, *, want_lse=True):
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, batch, seq, heads, head_dim, *, dbias=None):
-    """dqkv; with ``dbias`` (f32 [3E], accumulated into) the same kernel also reduces the column sums of dqkv."""
+def attention_bwd(qkv, out, dout, lse, batch, seq, heads, head_dim, *, dbias=None, delta=None):
+    """dqkv; with ``dbias`` (f32 [3E], accumulated into) the same kernel also reduces the column sums of dqkv. ``delta``
+    (f32 [batch, heads, seq] = rowsum(dout * out) per head, e.g. from the ROWDOT epilogue of the GEMM that produced
+    ``dout``): ``out`` is then not read and no delta pass is launched."""
     dqkv = torch.empty_like(qkv)
+    if delta is not None:
+        _req(delta, torch.float32, "delta")
+        assert delta.numel() == batch * heads * seq and delta.is_contiguous()
+        if dbias is not None:
+            _req(dbias, torch.float32, "dbias")
+        _check(
+            lib().vb_attention_bwd_with_delta(qkv.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), _ptr(dbias), delta.data_ptr(), batch, seq, heads, head_dim, _stream()),
+            "vb_attention_bwd_with_delta",
+        )
+        return dqkv
     ws = torch.empty(int(lib().vb_attention_bwd_workspace_bytes(batch, seq, heads)), device=qkv.device, dtype=torch.uint8)
     if dbias is not None:
         _req(dbias, torch.float32, "dbias")

@@ -540,6 +540,18 @@ extern "C" int vb_attention_bwd_bias(const void* qkv, const void* out, const voi
     return launch_colsum_bf16(static_cast<const bf16*>(dqkv), 3LL * heads * head_dim, dbias, batch * seq, 3 * heads * head_dim, stream);
 }
 
+extern "C" int vb_attention_bwd_with_delta(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias,
+                                           const void* workspace, int32_t batch, int32_t seq, int32_t heads,
+                                           int32_t head_dim, vb_stream_t stream_) {
+    using namespace vb;
+    VB_CHECK_ARG(qkv && dout && lse && dqkv && workspace, "vb_attention_bwd_with_delta: null pointer");
+    VB_CHECK_ARG(head_dim == HD, "vb_attention_bwd_with_delta: head_dim must be 64 (got %d)", head_dim);
+    VB_CHECK_ARG(batch > 0 && heads > 0 && seq > 0 && seq <= 208, "vb_attention_bwd_with_delta: seq=%d must be in [1, 208]", seq);
+    return launch_attention_bwd_tc3(static_cast<const bf16*>(qkv), nullptr, static_cast<const bf16*>(dout), lse,
+                                    static_cast<float*>(const_cast<void*>(workspace)), static_cast<bf16*>(dqkv), dbias, batch, seq, heads,
+                                    static_cast<cudaStream_t>(stream_));
+}
+
 static int attention_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace,
                                   int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, float* dbias, bool* dbias_done,
                                   cudaStream_t stream) {

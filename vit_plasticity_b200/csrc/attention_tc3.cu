@@ -1232,8 +1232,10 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
     rc = set_smem(attention_bwd_persistent_kernel, B_SMEM, done);
     if (rc) return rc;
     const int rows = batch * L;
-    attention_delta_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(out, dout, delta, rows, L, H);
-    VB_CHECK_LAUNCH();
+    if (out != nullptr) {  // (nullptr: the caller already left delta in the workspace, e.g. from the proj-dgrad epilogue)
+        attention_delta_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(out, dout, delta, rows, L, H);
+        VB_CHECK_LAUNCH();
+    }
     const int n_items = batch * H;
     const int grid = n_items < num_sms() ? n_items : num_sms();
     static const bool dbg_on = getenv("VITB200_DBG_TIMING") != nullptr;  // development only

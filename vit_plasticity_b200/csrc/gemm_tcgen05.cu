@@ -102,7 +102,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* aux_bar = bars + 2 * MAX_STAGES + 6;   // [EPI_WARPS][4]  TMA (aux chunk) -> epilogue warp, AUX_TMA only
     // The residual / saved-GELU' operand of the epilogue comes in through TMA, straight into the staging buffer the output
     // chunk leaves from: two chunks ahead, no per-lane strided global loads, the result overwrites it in place.
-    constexpr bool AUX_TMA = G == 2 && DEEP == 1 && (EPI_T == VB_EPI_BF16_RESID || EPI_T == VB_EPI_BF16_MULAUX);
+    constexpr bool AUX_TMA = G == 2 && DEEP == 1 && (EPI_T == VB_EPI_BF16_RESID || EPI_T == VB_EPI_BF16_MULAUX || EPI_T == VB_EPI_BF16_ROWDOT);
     // rank of this CTA in its pair (0 = leader: issues the MMAs); work is distributed over pairs
     const int rank = G == 2 ? static_cast<int>(cluster_ctarank()) : 0;
     const int unit = static_cast<int>(blockIdx.x) / G, num_units = static_cast<int>(gridDim.x) / G;
@@ -268,7 +268,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int hf = ew >> 2;   // which 128-column half of the tile
         uint8_t* stg = staging_base + ew * STAGING;
         const int epi = EPI_T >= 0 ? EPI_T : p.epi;
-        const bool has_aux = (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX);
+        const bool has_aux = (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX || epi == VB_EPI_BF16_ROWDOT);
         const bool two = (epi == VB_EPI_BF16_GELU || epi == VB_EPI_BF16_GELU_GRAD) && p.has_out2;
         const bool add_bias = p.bias != nullptr && epi != VB_EPI_F32_ADD && epi != VB_EPI_SUMSQ && epi != VB_EPI_BF16_DGELU &&
                               epi != VB_EPI_BF16_MULAUX;
@@ -331,6 +331,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
 
             float sumsq_local = 0.f;
+            float rowdot = 0.f;  // ROWDOT: this row's partial sum over the current 64-column group (two chunks)
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + hf * 128;
 
             // one 32-column chunk, accumulator values in v (as loaded from TMEM)
@@ -431,6 +432,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int j = 0; j < 16; ++j) {
                             const float2 g = unpack_bf16x2(ax[j]);
                             o[j] = pack_bf16x2(f[2 * j] * g.x, f[2 * j + 1] * g.y);
+                        }
+                    } else if (epi == VB_EPI_BF16_ROWDOT) {
+                        const uint32_t* ax = AUX_TMA ? axs : reinterpret_cast<const uint32_t*>(aux_cur);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                            const float2 v = unpack_bf16x2(o[j]), w = unpack_bf16x2(ax[j]);  // the values as stored
+                            rowdot = fmaf(v.x, w.x, fmaf(v.y, w.y, rowdot));
+                        }
+                        if (c & 1) {  // second half of a 64-column group: one plain store per (row, group)
+                            if (row_ok) {
+                                const int sample = row / p.rows_per_sample, q = row - sample * p.rows_per_sample;
+                                p.sumsq[((long long)sample * p.n_groups + (col0 >> 6)) * p.rows_per_sample + q] = rowdot;
+                            }
+                            rowdot = 0.f;
                         }
                     } else if (epi == VB_EPI_BF16_GELU_GRAD) {
 #pragma unroll
@@ -629,7 +645,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     VB_CHECK_ARG(a->a && a->b, "vb_gemm_bf16: null operand");
     VB_CHECK_ARG(a->a_layout == 0 || a->a_layout == 1, "vb_gemm_bf16: bad a_layout %d", a->a_layout);
     VB_CHECK_ARG(a->b_layout == 0 || a->b_layout == 1, "vb_gemm_bf16: bad b_layout %d", a->b_layout);
-    VB_CHECK_ARG(a->epilogue >= VB_EPI_BF16 && a->epilogue <= VB_EPI_BF16_MULAUX, "vb_gemm_bf16: bad epilogue %d",
+    VB_CHECK_ARG(a->epilogue >= VB_EPI_BF16 && a->epilogue <= VB_EPI_BF16_ROWDOT, "vb_gemm_bf16: bad epilogue %d",
                  a->epilogue);
     VB_CHECK_ARG(a->n % 8 == 0, "vb_gemm_bf16: n=%d must be a multiple of 8", a->n);
     const int epi = a->epilogue;
@@ -657,7 +673,10 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
         }
     }
     VB_CHECK_ARG(split_k == 1 || epi == VB_EPI_F32_ADD, "vb_gemm_bf16: split_k > 1 needs VB_EPI_F32_ADD");
-    if (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX)
+    if (epi == VB_EPI_BF16_ROWDOT)
+        VB_CHECK_ARG(a->sumsq && a->rows_per_sample > 0 && a->cols_per_group == 64 && a->n % 64 == 0 && a->n_groups == a->n / 64,
+                     "vb_gemm_bf16: ROWDOT needs sumsq, rows_per_sample, cols_per_group == 64, n %% 64 == 0, n_groups == n / 64");
+    if (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX || epi == VB_EPI_BF16_ROWDOT)
         VB_CHECK_ARG(a->aux != nullptr && a->ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,
                      "vb_gemm_bf16: aux must be non-null, 16B aligned, ld multiple of 8");
     if (epi == VB_EPI_SUMSQ)
@@ -669,7 +688,8 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     if (epi == VB_EPI_BF16_GELU_GRAD) VB_CHECK_ARG(a->out2 != nullptr, "vb_gemm_bf16: GELU_GRAD epilogue needs out2");
     if (a->bias) VB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "vb_gemm_bf16: bias must be 16B aligned");
     if (a->out_colsum)
-        VB_CHECK_ARG(epi == VB_EPI_BF16 || epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX,
+        VB_CHECK_ARG(epi == VB_EPI_BF16 || epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX ||
+                         epi == VB_EPI_BF16_ROWDOT,
                      "vb_gemm_bf16: out_colsum needs a single-output bf16 epilogue");
 
     CUtensorMap tmA, tmB, tmC, tmC2;
@@ -710,7 +730,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     }
 
     CUtensorMap tmAux = tmC;  // residual / saved-GELU' operand, read through TMA by the pair kernels of those epilogues
-    if (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_MULAUX) {
+    if (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_MULAUX || epi == VB_EPI_BF16_ROWDOT) {
         rc = make_tensor_map_2d(&tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->aux, a->n, a->m, a->ld_aux * 2, 32, 32,
                                 CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
@@ -762,6 +782,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
         if (al == 0 && bl == 1) {
             if (epi == VB_EPI_BF16) VB_LAUNCH_PAIR(0, 1, VB_EPI_BF16, 0);
             if (epi == VB_EPI_BF16_MULAUX) VB_LAUNCH_PAIR(0, 1, VB_EPI_BF16_MULAUX, 1);
+            if (epi == VB_EPI_BF16_ROWDOT) VB_LAUNCH_PAIR(0, 1, VB_EPI_BF16_ROWDOT, 1);
             VB_LAUNCH(0, 1, 2, -1, 0);
         }
         if (al == 1 && bl == 1) {

@@ -19,12 +19,15 @@ from __future__ import annotations
 
 import weakref
 
+import os
+
 import torch
 from torch.autograd import Function
 
 from . import _lib as L
 
 NUM_SMS = 148
+_FUSED_DELTA = os.environ.get("VB_FUSED_DELTA", "1") != "0"  # measurement switch: 0 = stand-alone delta pass
 
 # --------------------------------------------------------------------------------------------------
 # bf16 shadow weights
@@ -114,12 +117,18 @@ def linear_fwd(x, w16, bias, *, residual=None, gelu=False, gelu_grad=False):
     return out
 
 
-def linear_dgrad(dy, w16, *, dgelu_z=None, mul=None, colsum=None):
+def linear_dgrad(dy, w16, *, dgelu_z=None, mul=None, colsum=None, rowdot=None):
     """dx = dy @ W (W stored [n_out, k_in], used as-is as an MN-major B operand); optional * gelu'(z) computed from a saved
     z (``dgelu_z``) or * a saved derivative (``mul``). ``colsum`` (f32 [k_in]) += column sums of dx, from the epilogue."""
     m, n_out = dy.shape
     k_in = w16.shape[1]
     dx = torch.empty(m, k_in, device=dy.device, dtype=torch.bfloat16)
+    if rowdot is not None:
+        # rowdot = (other [m, k_in] bf16, out f32 [m / rows, k_in / 64, rows], rows): per-row dot products of dx with
+        # ``other`` over 64-column groups, from the epilogue registers (the attention backward's delta when other = O)
+        other, dst, rows = rowdot
+        L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_ROWDOT, aux=other, out=dx, sumsq=dst, rows_per_sample=rows, cols_per_group=64, n_groups=k_in // 64)
+        return dx
     if mul is not None:
         L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=mul, out=dx, out_colsum=colsum)
     elif dgelu_z is not None:
@@ -201,11 +210,15 @@ def _attn_bwd(dout, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need, ba
     dbo = bias_grad(dout, params[3]) if need[4] else None
     if not (need[0] or need[1] or need[2]):
         return None, None, None, dwo, dbo
-    do = linear_dgrad(dout, wo16)
+    # delta[b, h, q] = sum_d dO O of the attention backward comes out of the proj-dgrad epilogue that produces dO (tcgen05
+    # attention path, seq <= 208); longer sequences let the attention entry point run its own delta pass
+    fused_delta = seq <= 208 and e % 64 == 0 and _FUSED_DELTA
+    delta = torch.empty(batch, heads, seq, device=qkv.device, dtype=torch.float32) if fused_delta else None
+    do = linear_dgrad(dout, wo16, rowdot=(o, delta, seq)) if fused_delta else linear_dgrad(dout, wo16)
     # the qkv bias gradient = column sums of dqkv: reduced inside the attention backward kernel while it drains dQ/dK/dV
     tbq = grad_target(params[1]) if need[2] else None
     dbqkv = tbq if tbq is not None else (torch.zeros(qkv.shape[1], device=qkv.device, dtype=torch.float32) if need[2] else None)
-    dqkv = L.attention_bwd(qkv, o, do, lse, batch, seq, heads, e // heads, dbias=dbqkv)
+    dqkv = L.attention_bwd(qkv, o, do, lse, batch, seq, heads, e // heads, dbias=dbqkv, delta=delta)
     if tbq is not None:
         grad_done(params[1])
         dbqkv = None
