@@ -601,10 +601,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
         attr_set[dev] = true;
     }
     const int total_work = p.num_m_blocks * p.num_n_blocks * p.split_k;
-    const int units = num_sms() / G;  // CTAs (G = 1) or CTA pairs (G = 2) resident at once
-    const int grid = (total_work < units ? total_work : units) * G;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
     cfg.stream = stream;
@@ -615,6 +612,25 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = G > 1 ? 1 : 0;
+    // CTAs (G = 1) or CTA pairs (G = 2) that can be resident at once. The tile loop strides statically over the grid, so a
+    // pair that only becomes resident after another one has EXITED would serialise its whole share: never launch more pairs
+    // than the device can co-schedule (asked once per kernel and device; 74 on a full B200).
+    static int max_units[64] = {0};
+    int units = num_sms() / G;
+    if (G > 1 && dev < 64) {
+        if (max_units[dev] == 0) {
+            int n = 0;
+            cfg.gridDim = dim3(units * G);
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+                (void)cudaGetLastError();
+                n = units;
+            }
+            max_units[dev] = n;
+        }
+        if (max_units[dev] < units) units = max_units[dev];
+    }
+    const int grid = (total_work < units ? total_work : units) * G;
+    cfg.gridDim = dim3(grid);
     VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, tmAux, p));
     VB_CHECK_LAUNCH();
     return VB_OK;
