@@ -54,6 +54,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+#ifndef VB_MBAR_BACKOFF_NS
+#define VB_MBAR_BACKOFF_NS 0
+#endif
 // Bounded wait: a pipeline bug must surface as a trap (launch failure), never as a hung GPU box.
 #ifndef VB_MBAR_TIMEOUT_NS
 #define VB_MBAR_TIMEOUT_NS 4000000000ULL
@@ -82,6 +85,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     uint64_t t0 = globaltimer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+#if VB_MBAR_BACKOFF_NS > 0
+        __nanosleep(VB_MBAR_BACKOFF_NS);  // waiting warps give their issue slots to the warps that share the scheduler
+#endif
         if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > VB_MBAR_TIMEOUT_NS) mbar_timeout_trap(tag, parity);
     }
 }
