@@ -58,18 +58,22 @@ def workload_config(model_name: str, batch: int, world: int, comps, n_trainable=
 
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, averaged over the launches of the committed
-    `ncu --set full` capture of this command (profiles/*ncu_full_gemm*.txt); None if no capture is committed."""
+    `ncu --set full` captures of this command (the latest round's profiles/*ncu_full_gemm*.txt: forward launches and the
+    backward launches of one block); None if no capture is committed."""
     files = sorted((ROOT / "profiles").glob("*ncu_full_gemm*.txt"))
     if not files:
         return None, None
+    prefix = files[-1].name.split("_ncu_full_gemm")[0]  # e.g. "r02_z"
+    files = [f for f in files if f.name.startswith(prefix + "_ncu_full_gemm")]
     tot, n = 0.0, 0
-    for line in files[-1].read_text().splitlines():
-        parts = line.split()
-        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            val, unit = float(parts[1]), parts[2]
-            tot += val * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
-            n += 1
-    return (tot / (n / 2) if n else None), files[-1].name
+    for f in files:
+        for line in f.read_text().splitlines():
+            parts = line.split()
+            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                val, unit = float(parts[1]), parts[2]
+                tot += val * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
+                n += 1
+    return (tot / (n / 2) if n else None), " + ".join(f.name for f in files)
 
 
 def peaks():

@@ -20,6 +20,6 @@ if [ "$2" == "ncu" ]; then
   $BCMD > gpurun_out/${tag}_ncu_plain2.log 2>&1 &&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 150 -c 6 -o gpurun_out/${tag}_prof_gemm $BCMD > gpurun_out/${tag}_ncu_full.log 2>&1
   echo "ncu full rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_bwd_persistent -s 13 -c 2 -o gpurun_out/${tag}_prof_attn_bwd $BCMD > gpurun_out/${tag}_ncu_full_attn.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_bwd_ -s 13 -c 2 -o gpurun_out/${tag}_prof_attn_bwd $BCMD > gpurun_out/${tag}_ncu_full_attn.log 2>&1
   echo "ncu full (attention bwd) rc=$?"
 fi
