@@ -133,6 +133,35 @@ def test_gemm_residual():
     _report("gemm_resid", out, ref, atol=3e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("m,n,k", [(300, 136, 192), (257, 768, 768), (1000, 520, 64)])
+def test_gemm_residual_short_k_ragged(m, n, k):
+    """K < 2048 takes the TMA-fed residual path of the pair kernel: ragged M (odd CTA of the last pair partly / wholly
+    beyond M) and N that ends inside a 32-column chunk."""
+    L = _lib()
+    a = _rand(m, k, seed=1).bfloat16()
+    b = _rand(n, k, seed=2, scale=0.05).bfloat16()
+    bias = _rand(n, seed=3)
+    res = _rand(m, n, seed=4).bfloat16()
+    out = torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16)
+    L.gemm(a, b, m=m, n=n, k=k, epilogue=L.EPI_BF16_RESID, bias=bias, aux=res, out=out)
+    torch.cuda.synchronize()
+    _report("gemm_resid_ragged", out, a.float() @ b.float().T + bias + res.float(), atol=3e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("tokens,n_out,k_in", [(333, 136, 200), (130, 64, 72)])
+def test_gemm_dgrad_mulaux_ragged(tokens, n_out, k_in):
+    L = _lib()
+    dy = _rand(tokens, n_out, seed=1).bfloat16()
+    w = _rand(n_out, k_in, seed=2, scale=0.05).bfloat16()
+    z = _rand(tokens, k_in, seed=3).bfloat16()
+    out = torch.full((tokens, k_in), float("nan"), device=DEV, dtype=torch.bfloat16)
+    cs = torch.zeros(k_in, device=DEV, dtype=torch.float32)
+    L.gemm(dy, w, m=tokens, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=z, out=out, out_colsum=cs)
+    torch.cuda.synchronize()
+    _report("dgrad_mulaux_ragged", out, (dy.float() @ w.float()) * z.float(), atol=3e-2, rtol=1e-2)
+    _report("dgrad_mulaux_ragged_colsum", cs, out.float().sum(0), atol=2e-3, rtol=1e-4)
+
+
 def test_gemm_gelu_two_outputs():
     L = _lib()
     m, n, k = 394, 3072, 768
