@@ -100,6 +100,11 @@ int vb_gemm_bf16(const vb_gemm_args* args, vb_stream_t stream);
  * split_k == 1 (same k order); the setting exists for measurement and bisection. */
 void vb_set_gemm_cta_pair(int mode);
 int vb_get_gemm_cta_pair(void);
+/* Tile order of vb_gemm_bf16: 0 (default; env VB_GEMM_DYNAMIC=1 overrides) = every CTA pair strides statically over the
+ * tiles, 1 = work stealing: tile indices are drawn from a per-launch device counter, so CTAs that become resident late
+ * (SMs held by a concurrent kernel such as an overlapped all-reduce) do not delay the launch. Same results either way. */
+void vb_set_gemm_scheduler(int dynamic);
+int vb_get_gemm_scheduler(void);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm (nn.LayerNorm, transformer/utils.py:293; used at architecture.py:347,349 and utils.py:396)

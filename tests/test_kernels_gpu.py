@@ -54,20 +54,22 @@ def _report(name, got, ref, atol, rtol):
 # ---------------------------------------------------------------------------------------------------
 # GEMM
 # ---------------------------------------------------------------------------------------------------
-@pytest.fixture(autouse=True, params=["pair", "single"])
+@pytest.fixture(autouse=True, params=["pair", "single", "pair+steal", "single+steal"])
 def _gemm_tile_mapping(request):
-    """Every GEMM test runs under both tile mappings: CTA pairs (256 x 256, tcgen05 cta_group::2; the default) and single
-    CTAs (128 x 256). Non-GEMM tests run once."""
+    """Every GEMM test runs under both tile mappings — CTA pairs (256 x 256, tcgen05 cta_group::2; the default) and single
+    CTAs (128 x 256) — and under both tile orders (static stride, work stealing). Non-GEMM tests run once."""
     if not request.node.name.startswith("test_gemm"):
-        if request.param == "single":
-            pytest.skip("tile mapping only concerns the GEMM tests")
+        if request.param != "pair":
+            pytest.skip("tile mapping / order only concern the GEMM tests")
         yield
         return
     lib = _lib().lib()
-    before = lib.vb_get_gemm_cta_pair()
-    lib.vb_set_gemm_cta_pair(1 if request.param == "pair" else 0)
+    before, before_s = lib.vb_get_gemm_cta_pair(), lib.vb_get_gemm_scheduler()
+    lib.vb_set_gemm_cta_pair(1 if request.param.startswith("pair") else 0)
+    lib.vb_set_gemm_scheduler(1 if request.param.endswith("+steal") else 0)
     yield
     lib.vb_set_gemm_cta_pair(before)
+    lib.vb_set_gemm_scheduler(before_s)
 
 
 def test_gemm_pair_and_single_mappings_agree_bitwise():

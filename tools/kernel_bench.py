@@ -35,7 +35,7 @@ def timeit(fn, iters=10, warm=3):
 
 
 MODES = [int(c) for c in os.environ.get("KB_GEMM_MODES", "")] if os.environ.get("KB_GEMM_MODES") else None
-MODE_NAMES = {0: "single", 1: "pair", 2: "pair/6-stage", 3: "pair/5-stage"}
+MODE_NAMES = {0: "single", 1: "pair", 2: "pair/6-stage", 3: "pair/5-stage", 4: "pair+steal"}
 
 
 def timeit_gemm(name, fn, flops):
@@ -47,10 +47,12 @@ def timeit_gemm(name, fn, flops):
     before = L.lib().vb_get_gemm_cta_pair()
     parts = []
     for mode in MODES:
-        L.lib().vb_set_gemm_cta_pair(mode)
+        L.lib().vb_set_gemm_cta_pair(1 if mode == 4 else mode)
+        L.lib().vb_set_gemm_scheduler(1 if mode == 4 else 0)
         ms = timeit(fn)
         parts.append(f"{MODE_NAMES[mode]} {ms*1e3:7.1f} us ({flops / ms / 1e9:6.0f} TF)")
     L.lib().vb_set_gemm_cta_pair(before)
+    L.lib().vb_set_gemm_scheduler(0)
     print(f"{name:34s} " + " | ".join(parts), flush=True)
 
 

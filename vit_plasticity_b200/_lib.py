@@ -73,6 +73,8 @@ SIGNATURES = {
     ),
     "vb_set_gemm_cta_pair": (None, [c_int32]),
     "vb_get_gemm_cta_pair": (c_int32, []),
+    "vb_set_gemm_scheduler": (None, [c_int32]),
+    "vb_get_gemm_scheduler": (c_int32, []),
     "vb_layernorm_fwd": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p],

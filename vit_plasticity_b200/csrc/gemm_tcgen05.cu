@@ -37,6 +37,7 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * STAGING_BYTES + 512 + 1024;  // + barriers + alignment slack
 };
 constexpr int MAX_STAGES = 6;
+constexpr int SCHED_SLOTS = 4;  // tile indices in flight between the fetcher and the slowest role (the epilogue)
 
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_FIRST_WARP = 4;
@@ -57,6 +58,8 @@ struct GemmKernelParams {
     int rows_per_sample, cols_per_group, n_groups;
     int has_out2;
     float* out_colsum;  // f32 [N] or null: += column sums of the bf16 output (bias gradient of the layer that produced A's grad)
+    unsigned* sched;        // work-stealing tile scheduler: this launch's tile counter (starts at 0), or null = static stride
+    unsigned* sched_clear;  // a counter slot of a FUTURE launch, zeroed by this one
 };
 
 struct WorkItem {
@@ -100,6 +103,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;  // [2]     epilogue -> MMA (G = 2: both CTAs' warps arrive on the leader's)
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
     uint64_t* aux_bar = bars + 2 * MAX_STAGES + 6;   // [EPI_WARPS][4]  TMA (aux chunk) -> epilogue warp, AUX_TMA only
+    uint64_t* sched_full = bars + 2 * MAX_STAGES + 6 + EPI_WARPS * 4;  // [SCHED_SLOTS] fetcher -> every role of both CTAs
+    uint64_t* sched_empty = sched_full + SCHED_SLOTS;                  // [SCHED_SLOTS] (leader's) every role -> fetcher
+    volatile int* sched_ids = reinterpret_cast<volatile int*>(sched_empty + SCHED_SLOTS);  // [SCHED_SLOTS] tile index or -1
     // The residual / saved-GELU' operand of the epilogue comes in through TMA, straight into the staging buffer the output
     // chunk leaves from: two chunks ahead, no per-lane strided global loads, the result overwrites it in place.
     constexpr bool AUX_TMA = G == 2 && DEEP == 1 && (EPI_T == VB_EPI_BF16_RESID || EPI_T == VB_EPI_BF16_MULAUX || EPI_T == VB_EPI_BF16_ROWDOT);
@@ -129,6 +135,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (AUX_TMA)
             for (int a = 0; a < EPI_WARPS * 4; ++a) mbar_init(&aux_bar[a], 1);
+        for (int a = 0; a < SCHED_SLOTS; ++a) {
+            mbar_init(&sched_full[a], 1);
+            // consumers of a tile index: TMA warp + 8 epilogue warps of each CTA, + the leader's MMA warp
+            mbar_init(&sched_empty[a], G * (1 + EPI_WARPS) + 1);
+        }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -152,6 +163,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int total_work = p.num_m_blocks * p.num_n_blocks * p.split_k;
 
+    // Tile order. Static: pair u takes tiles u, u + num_units, ... Work-stealing (p.sched != null): warp 3 of the leader CTA
+    // draws tile indices from a global counter and hands each one to every role of both CTAs through a 4-slot ring, so a
+    // CTA pair that becomes resident late (SMs held by another kernel, e.g. an overlapped all-reduce) finds the remaining
+    // tiles already taken instead of running its whole static share after everybody else has finished.
+    const bool dyn = p.sched != nullptr;
+    struct TileIter {
+        int w, slot;
+        uint32_t ph;
+    };
+    auto next_tile = [&](TileIter& ti) -> int {
+        if (!dyn) {
+            const int r = ti.w < total_work ? ti.w : -1;
+            ti.w += num_units;
+            return r;
+        }
+        mbar_wait(&sched_full[ti.slot], ti.ph, 6);
+        const int tile = sched_ids[ti.slot];
+        __syncwarp();
+        if (elect_one()) {
+            if (G == 1)
+                mbar_arrive(&sched_empty[ti.slot]);
+            else
+                mbar_arrive_leader(&sched_empty[ti.slot]);
+        }
+        if (++ti.slot == SCHED_SLOTS) ti.slot = 0, ti.ph ^= 1;
+        return tile;
+    };
     // The producer and MMA warps run their loops with ALL 32 lanes in uniform control flow and elect one lane only
     // around the asynchronous instructions: addresses / descriptors stay in uniform registers. (With the whole loop
     // under `if (lane == 0)` the compiler wrapped every UTCHMMA / UTMALDG in a divergence "waterfall" loop of ~20
@@ -168,7 +206,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             else
                 tma_load_2d_pair(dst, map, bar, c0, c1);
         };
-        for (int w = unit; w < total_work; w += num_units) {
+        TileIter ti = {unit, 0, 0};
+        for (int w = next_tile(ti); w >= 0; w = next_tile(ti)) {
             const WorkItem it = decode_work<G>(p, w, rank);
             const int n0 = it.n_blk * BN + rank * (BN / G);  // this CTA's share of the B tile
             for (int kb = it.kb0; kb < it.kb1; ++kb) {
@@ -211,7 +250,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int w = unit; w < total_work; w += num_units) {
+        TileIter ti = {unit, 0, 0};
+        for (int w = next_tile(ti); w >= 0; w = next_tile(ti)) {
             const WorkItem it = decode_work<G>(p, w, rank);
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
             tc_fence_after();
@@ -256,6 +296,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+    } else if (warp == 3 && rank == 0 && dyn) {
+        // =========================== tile fetcher (work-stealing scheduler) ===========================
+        if (lane == 0) {
+            if (blockIdx.x == 0) *p.sched_clear = 0u;  // the counter of a launch far in the future
+            int slot = 0;
+            uint32_t ph = 0;
+            while (true) {
+                mbar_wait(&sched_empty[slot], ph ^ 1, 7);
+                const unsigned t = atomicAdd(p.sched, 1u);
+                const int tile = t < static_cast<unsigned>(total_work) ? static_cast<int>(t) : -1;
+                const uint32_t id_addr = smem_u32(const_cast<int*>(&sched_ids[slot])), full_addr = smem_u32(&sched_full[slot]);
+                if (G == 1) {
+                    sched_ids[slot] = tile;
+                    mbar_arrive(&sched_full[slot]);  // (release at CTA scope orders the store before it)
+                } else {
+                    for (int r = 0; r < G; ++r) {  // asynchronous store + transaction count: waiters need no cluster-scope acquire
+                        const uint32_t bar_r = mapa_u32(full_addr, r);
+                        mbar_arrive_expect_tx_cluster(bar_r, 4);
+                        st_async_u32(mapa_u32(id_addr, r), static_cast<uint32_t>(tile), bar_r);
+                    }
+                }
+                if (tile < 0) break;
+                if (++slot == SCHED_SLOTS) slot = 0, ph ^= 1;
+            }
+        }
+        __syncwarp();
     }
     } else {
         // =========================== epilogue ===========================
@@ -288,15 +354,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
         };
         uint32_t tchunk = 0;
-        if (AUX_TMA && unit < total_work) {
-            const WorkItem first = decode_work<G>(p, unit, rank);
+        TileIter ti = {unit, 0, 0};
+        int w = next_tile(ti);
+        int w_next = w >= 0 ? next_tile(ti) : -1;  // the epilogue looks one tile ahead (aux prefetch)
+        if (AUX_TMA && w >= 0) {
+            const WorkItem first = decode_work<G>(p, w, rank);
             request_aux(first, 0, 0);
             request_aux(first, 1, 1);
         }
-        for (int w = unit; w < total_work; w += num_units) {
+        for (; w >= 0; w = w_next, w_next = (w >= 0 ? next_tile(ti) : -1)) {
             const WorkItem it = decode_work<G>(p, w, rank);
-            const bool have_next = w + num_units < total_work;
-            const WorkItem nxt_it = (AUX_TMA && have_next) ? decode_work<G>(p, w + num_units, rank) : it;
+            const bool have_next = w_next >= 0;
+            const WorkItem nxt_it = (AUX_TMA && have_next) ? decode_work<G>(p, w_next, rank) : it;
             const int row0 = it.m_blk * BM + q * 32;
             const int row = row0 + lane;
             const int colbase = it.n_blk * BN + hf * 128;
@@ -314,11 +383,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             };
             if (!AUX_TMA) load_aux(aux_cur, colbase);  // issued before the accumulator wait: latency hides behind the MMA
-            if (!AUX_TMA && has_aux && w + num_units < total_work) {
+            if (!AUX_TMA && has_aux && have_next) {
                 // The aux rows of this CTA's NEXT tile go to L2 now: a whole main loop ahead of their use, so the
                 // per-chunk loads above hit L2 (~300 cycles) instead of HBM (~1500), which had made the short-K
                 // residual / GELU' epilogues latency-bound (proj forward: 136 us against 93 us without epilogue).
-                const WorkItem nx = decode_work<G>(p, w + num_units, rank);
+                const WorkItem nx = decode_work<G>(p, w_next, rank);
                 const int nrow = nx.m_blk * BM + q * 32 + lane, ncol = nx.n_blk * BN + hf * 128;
                 if (nrow < p.M && ncol < p.N) {
                     const bf16* pa = p.aux + (long long)nrow * p.ld_aux + ncol;
@@ -636,6 +705,37 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     return VB_OK;
 }
 
+// Work-stealing tile scheduler: a ring of per-launch tile counters per device. Launch number s uses slot s % R (zero: cleared
+// by launch s - R/2, or by the initial memset) and clears slot (s + R/2) % R for a later launch, so there is no per-launch
+// memset and no host-side bookkeeping of counter values; correct as long as fewer than R/2 GEMM launches of one device are
+// in flight at once. Off by default (VB_GEMM_DYNAMIC=1 or vb_set_gemm_scheduler(1) turns it on).
+constexpr int SCHED_RING = 1024;
+static unsigned* g_sched_ring[64] = {nullptr};
+static unsigned long long g_sched_seq[64] = {0};
+static int g_dynamic = -1;
+static int dynamic_enabled() {
+    if (g_dynamic < 0) {
+        const char* e = getenv("VB_GEMM_DYNAMIC");
+        g_dynamic = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return g_dynamic;
+}
+static int sched_slots(unsigned** cur, unsigned** clear) {
+    int dev = 0;
+    VB_CHECK_CUDA(cudaGetDevice(&dev));
+    *cur = *clear = nullptr;
+    if (!dynamic_enabled() || dev >= 64) return VB_OK;
+    if (g_sched_ring[dev] == nullptr) {
+        VB_CHECK_CUDA(cudaMalloc(&g_sched_ring[dev], SCHED_RING * sizeof(unsigned)));
+        VB_CHECK_CUDA(cudaMemset(g_sched_ring[dev], 0, SCHED_RING * sizeof(unsigned)));
+        VB_CHECK_CUDA(cudaDeviceSynchronize());
+    }
+    const unsigned long long s = g_sched_seq[dev]++;
+    *cur = g_sched_ring[dev] + (s % SCHED_RING);
+    *clear = g_sched_ring[dev] + ((s + SCHED_RING / 2) % SCHED_RING);
+    return VB_OK;
+}
+
 // 0 = single CTAs (128 x 256); 1 = CTA pairs (256 x 256 tiles, cta_group::2) with the ring / staging split chosen per
 // epilogue; 2 / 3 = pairs with the 6-stage / 5-stage split forced everywhere (measurement only).
 // Default from VB_GEMM_CTA_PAIR (1 if unset).
@@ -652,6 +752,8 @@ static int cta_pair_enabled() {
 
 extern "C" void vb_set_gemm_cta_pair(int mode) { vb::g_cta_pair = (mode >= 0 && mode <= 3) ? mode : 1; }
 extern "C" int vb_get_gemm_cta_pair(void) { return vb::cta_pair_enabled(); }
+extern "C" void vb_set_gemm_scheduler(int dynamic) { vb::g_dynamic = dynamic ? 1 : 0; }
+extern "C" int vb_get_gemm_scheduler(void) { return vb::dynamic_enabled(); }
 
 extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     using namespace vb;
@@ -772,6 +874,8 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     p.n_groups = a->n_groups;
     p.has_out2 = a->out2 != nullptr;
     p.out_colsum = a->out_colsum;
+    rc = sched_slots(&p.sched, &p.sched_clear);
+    if (rc) return rc;
 
     // the hot combinations of the training step get an epilogue fixed at compile time, everything else the generic kernel
 #define VB_LAUNCH(AL, BL, GG, EP, DP) return launch_gemm<AL, BL, GG, EP, DP>(tmA, tmB, tmC, tmC2, tmAux, p, stream)
