@@ -54,20 +54,24 @@ def _report(name, got, ref, atol, rtol):
 # ---------------------------------------------------------------------------------------------------
 # GEMM
 # ---------------------------------------------------------------------------------------------------
-@pytest.fixture(autouse=True, params=["pair", "single", "pair+steal", "single+steal"])
-def _gemm_tile_mapping(request):
+GEMM_MODES = ["pair", "single", "pair+steal", "single+steal"]
+
+
+def pytest_generate_tests(metafunc):
     """Every GEMM test runs under both tile mappings — CTA pairs (256 x 256, tcgen05 cta_group::2; the default) and single
-    CTAs (128 x 256) — and under both tile orders (static stride, work stealing). Non-GEMM tests run once."""
-    if not request.node.name.startswith("test_gemm"):
-        if request.param != "pair":
-            pytest.skip("tile mapping / order only concern the GEMM tests")
-        yield
-        return
+    CTAs (128 x 256) — and under both tile orders (static stride, work stealing). Other tests run once."""
+    if metafunc.function.__name__.startswith("test_gemm"):
+        metafunc.fixturenames.append("_gemm_mode")
+        metafunc.parametrize("_gemm_mode", GEMM_MODES, indirect=True)
+
+
+@pytest.fixture
+def _gemm_mode(request):
     lib = _lib().lib()
     before, before_s = lib.vb_get_gemm_cta_pair(), lib.vb_get_gemm_scheduler()
     lib.vb_set_gemm_cta_pair(1 if request.param.startswith("pair") else 0)
     lib.vb_set_gemm_scheduler(1 if request.param.endswith("+steal") else 0)
-    yield
+    yield request.param
     lib.vb_set_gemm_cta_pair(before)
     lib.vb_set_gemm_scheduler(before_s)
 
