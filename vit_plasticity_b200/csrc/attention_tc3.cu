@@ -12,13 +12,15 @@
 // forward, per item two units (query tiles of 128 rows): S = Q_t K^T (N = 208) -> exact softmax, one TMEM read, the row
 //   split over 4 warps (64+48+48+48 columns held in registers) -> O = P V.
 //   TMEM: S/P buffers [0,208) and [208,416) (unit parity), O accumulator [416,480).
-// backward, per item four units: dQ_t (t = 0,1; queries on the TMEM lanes) and dK_j/dV_j (j = 0,1; keys on the lanes,
+// backward: attention_bwd_kd_kernel (key-domain schedule, the default; described at its definition below). The earlier
+// two-domain kernel (attention_bwd_persistent_kernel, kept behind VITB200_ATTN_BWD=old for bisection) works as follows:
+//   per item four units: dQ_t (t = 0,1; queries on the TMEM lanes) and dK_j/dV_j (j = 0,1; keys on the lanes,
 //   "transposed domain", so lse / delta are per-COLUMN scalars there). Each unit walks 4 column chunks (64,64,64,16):
 //   MMA1: S_c, dP_c -> math: P = exp2(S c - lse), dS = P (dP - delta) / 8 -> MMA2: accumulate.
 //   TMEM: three chunk buffers [0,128) [128,256) [256,384) (S at +0, dP at +64), accumulator [384,512). Two issuer warps:
 //   warp 17 issues every MMA1 (three chunks ahead of the math), warp 18 every MMA2; a buffer returns to MMA1 when the
-//   MMA2 that read it has completed. The two math groups (8 warps each) take alternate chunks; group 1 also drains the
-//   accumulators. No masking is needed: padded K/V/Q/dO rows are zero and padded lse entries are +inf (p = 0).
+//   MMA2 that read it has completed. The two math groups (8 warps each) take alternate chunks; a separate drain warpgroup
+//   reads the accumulators out. No masking is needed: padded K/V/Q/dO rows are zero and padded lse entries are +inf (p = 0).
 //   Measured (tools/microbench/mma_rate.cu): a 128xNx16 MMA costs ~44 + N/2 cycles with A in smem, ~12 + N/2 with A in
 //   TMEM, so these N = 64 tiles run the tensor pipe at < 50 % of its rate: head_dim 64 bounds this kernel, not HBM.
 #include <stdlib.h>

@@ -1,16 +1,20 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:
-//   TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring -> tcgen05.mma (128x256x16, cta_group::1)
-//   -> double-buffered fp32 accumulators in TMEM (2 x 256 columns) -> tcgen05.ld epilogue on 8 warps
-//   -> swizzled smem staging -> TMA store / TMA reduce-add.
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared-memory ring -> tcgen05.mma -> double-buffered fp32 accumulators in
+//   TMEM (2 x 256 columns) -> tcgen05.ld epilogue on 8 warps -> swizzled smem staging -> TMA store / TMA reduce-add.
+// Tile mapping G: 2 (default) = a CTA pair (cluster of 2) per 256 x 256 tile, ONE tcgen05.mma.cta_group::2 256x256x16 per
+//   k-step, each CTA stages its own 128 rows of A and half of the B tile (6 x 32 KB ring, 5 for the two-output / aux
+//   epilogues); 1 = one CTA per 128 x 256 tile (cta_group::1, 4 x 48 KB ring).
 //
 // One kernel serves every dense contraction of the ViT hot path:
-//   forward  y  = x W^T (+bias, +GELU, +residual)     A K-major,  B K-major
-//   dgrad    dx = dy W  (x gelu'(z))                  A K-major,  B MN-major (weights used as stored)
-//   wgrad    dW += dy^T x  (split-K, TMA reduce-add)  A MN-major, B MN-major (activations used as stored)
+//   forward  y  = x W^T (+bias, +GELU(+GELU'), +residual)          A K-major,  B K-major
+//   dgrad    dx = dy W  (x gelu'(z), + row dots with a 2nd operand)  A K-major,  B MN-major (weights used as stored)
+//   wgrad    dW += dy^T x  (split-K, TMA reduce-add)                 A MN-major, B MN-major (activations used as stored)
 //   plasticity: sum of squares of the accumulator per sample, nothing written back
 //
-// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
-// warps 4..11 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the 128-column half of the tile).
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA of a pair), warp 2 = TMEM allocator,
+// warp 3 = tile fetcher of the optional work-stealing scheduler (else idle); warps 4..11 = epilogue (warp % 4 selects the
+// TMEM lane quarter, (warp - 4) / 4 the 128-column half of the tile). Registers: 56 for warps 0..3, 224 for the epilogue
+// (setmaxnreg; the kernel must stay free of CALLs for that, see ptx.cuh).
 #include "host_utils.h"
 #define VB_MBAR_TRAP_PRINTF 0  // no CALL in this kernel: see ptx.cuh (per-role register budgets via setmaxnreg)
 #include "ptx.cuh"
