@@ -22,7 +22,7 @@ def _make_model():
     return nn.Sequential(nn.Linear(16, 32), nn.GELU(), nn.Linear(32, 32), nn.LayerNorm(32), nn.Linear(32, 4))
 
 
-def _worker(rank, world, port, bucket_mb, freeze_first, outdir):
+def _worker(rank, world, port, bucket_mb, freeze_first, outdir, overlap=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     from vit_plasticity_b200.distributed import DataParallel
     from vit_plasticity_b200.finetune import train_step
@@ -37,7 +37,7 @@ def _worker(rank, world, port, bucket_mb, freeze_first, outdir):
         if freeze_first:
             for p in model[0].parameters():
                 p.requires_grad = False
-        dp = DataParallel(model, bucket_mb=bucket_mb)
+        dp = DataParallel(model, bucket_mb=bucket_mb, overlap=overlap)
         g = torch.Generator().manual_seed(1)
         x, y = torch.randn(8, 16, generator=g), torch.randint(0, 4, (8,), generator=g)
         lo, hi = rank * 4, rank * 4 + 4
@@ -56,11 +56,12 @@ def _worker(rank, world, port, bucket_mb, freeze_first, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("bucket_mb,freeze_first", [(64, False), (0.002, False), (0.002, True)])
-def test_two_rank_gloo_matches_single_process(bucket_mb, freeze_first, tmp_path):
+@pytest.mark.parametrize("bucket_mb,freeze_first,overlap", [(64, False, True), (0.002, False, True), (0.002, True, True), (0.002, True, False)])
+def test_two_rank_gloo_matches_single_process(bucket_mb, freeze_first, overlap, tmp_path):
+    """overlap=False: ONE all-reduce of the whole gradient arena after backward instead of one per bucket from the hooks."""
     ctx = mp.get_context("spawn")
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, bucket_mb, freeze_first, str(tmp_path))) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, bucket_mb, freeze_first, str(tmp_path), overlap)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
