@@ -226,6 +226,14 @@ int vb_sgd_momentum_clip_step(const void* chunk_table, int32_t n_chunks, const f
                               const float* sumsq_partials, int32_t n_partials, float* grad_norm_out, float max_norm, float lr,
                               float momentum, float weight_decay, int32_t first_step, vb_stream_t stream);
 
+/* AdamW (torch.optim.AdamW, amsgrad off: src/vitef/optim.py:83-88) over the same arenas, clip coefficient as above:
+ *   g = coef * grad;  p *= 1 - lr * weight_decay;  m += (1 - beta1)(g - m);  v = beta2 v + (1 - beta2) g^2;
+ *   p -= (lr / bias_correction1) * m / (sqrt(v) / sqrt(bias_correction2) + eps),  bias_correction_i = 1 - beta_i^step. */
+int vb_adamw_clip_step(const void* chunk_table, int32_t n_chunks, const float* grad_arena, float* exp_avg_arena,
+                       float* exp_avg_sq_arena, const float* sumsq_partials, int32_t n_partials, float* grad_norm_out,
+                       float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       float bias_correction1, float bias_correction2, vb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -481,3 +481,35 @@ def test_rowsumsq_and_ln_pair():
     zb = torch.nn.functional.layer_norm(b, (cols,), eps=1e-12)
     refu = ((za - zb) ** 2).reshape(s, rows, cols).sum(1)
     assert torch.allclose(u, refu, rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused optimizers over the flat gradient arena
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("opt_name", ["sgd", "adamw"])
+def test_fused_arena_optimizers_match_torch(opt_name):
+    """clip_grad_norm_(1.0) + torch.optim.{SGD(momentum 0.9), AdamW} against FusedSGD / FusedAdamW (one norm launch + one
+    update launch over the arena) on identical parameters and gradients, four steps; fp32 round-off tolerance."""
+    from vit_plasticity_b200.finetune import FusedAdamW, FusedSGD
+
+    shapes = [(257, 64), (64,), (1000, 33), (7,), (128, 128)]
+    g = torch.Generator().manual_seed(3)
+    ref = [torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for s in shapes]
+    got = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    if opt_name == "sgd":
+        o_ref, o_got = torch.optim.SGD(ref, lr=1e-2, momentum=0.9, weight_decay=1e-3), FusedSGD(got, lr=1e-2, momentum=0.9, weight_decay=1e-3)
+    else:
+        o_ref, o_got = torch.optim.AdamW(ref, lr=1e-3, weight_decay=1e-2), FusedAdamW(got, lr=1e-3, weight_decay=1e-2)
+    for step in range(4):
+        grads = [torch.randn(*s, generator=g).to(DEV) * (0.1 + step) for s in shapes]
+        for p, q, gr in zip(ref, got, grads):
+            p.grad = gr.clone()
+            q.grad.copy_(gr)  # FusedSGD keeps .grad as views of its arena
+        n_ref = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        o_ref.step()
+        n_got = o_got.step(max_norm=1.0)
+        o_got.zero_grad()
+        torch.cuda.synchronize()
+        assert abs(float(n_ref) - float(n_got)) <= 1e-5 * float(n_ref)
+        for p, q in zip(ref, got):
+            _report(f"{opt_name} step {step}", q.detach().reshape(1, -1), p.detach().reshape(1, -1), atol=2e-6, rtol=2e-5)

@@ -111,6 +111,48 @@ sgd_momentum_clip_kernel(const OptChunk* __restrict__ table, const float* __rest
     }
 }
 
+// AdamW (torch.optim.AdamW, amsgrad off; src/vitef/optim.py:83-88) with the same clip coefficient folded in:
+//   g <- coef g;  p <- p (1 - lr wd);  m <- m + (1 - b1)(g - m);  v <- b2 v + (1 - b2) g^2;
+//   p <- p - (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)          (bc1 = 1 - b1^t, bc2 = 1 - b2^t, computed by the host)
+__global__ void __launch_bounds__(OPT_THREADS)
+adamw_clip_kernel(const OptChunk* __restrict__ table, const float* __restrict__ grad, float* __restrict__ exp_avg,
+                  float* __restrict__ exp_avg_sq, const float* __restrict__ sumsq_partials, int n_partials,
+                  float* __restrict__ norm_out, float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float step_size, float inv_bc2_sqrt) {
+    __shared__ float red[OPT_THREADS / 32];
+    const OptChunk c = table[blockIdx.x];
+    float part = 0.f;
+    for (int i = threadIdx.x; i < n_partials; i += OPT_THREADS) part += __ldg(sumsq_partials + i);
+    const float norm = sqrtf(block_sum_deterministic(part, red));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out != nullptr) *norm_out = norm;
+    const float coef = fminf(1.f, max_norm / (norm + 1e-6f));
+    const float decay = 1.f - lr * weight_decay, omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+    const float* g = grad + c.arena_off;
+    float* m = exp_avg + c.arena_off;
+    float* v = exp_avg_sq + c.arena_off;
+    float* p = c.param;
+    auto upd = [&](float gi, float& mi, float& vi, float& pi) {
+        gi *= coef;
+        pi *= decay;
+        mi = fmaf(omb1, gi - mi, mi);
+        vi = fmaf(omb2 * gi, gi, beta2 * vi);
+        pi = fmaf(-step_size, mi / fmaf(sqrtf(vi), inv_bc2_sqrt, eps), pi);
+    };
+    const int n4 = c.count >> 2;
+    for (int i = threadIdx.x; i < n4; i += OPT_THREADS) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+        upd(g4.x, m4.x, v4.x, p4.x);
+        upd(g4.y, m4.y, v4.y, p4.y);
+        upd(g4.z, m4.z, v4.z, p4.z);
+        upd(g4.w, m4.w, v4.w, p4.w);
+        reinterpret_cast<float4*>(m)[i] = m4;
+        reinterpret_cast<float4*>(v)[i] = v4;
+        reinterpret_cast<float4*>(p)[i] = p4;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < c.count; i += OPT_THREADS) upd(g[i], m[i], v[i], p[i]);
+}
+
 }  // namespace vb
 
 extern "C" int vb_sumsq_partials_f32(const float* x, int64_t n, float* partials, int32_t n_partials, vb_stream_t stream_) {
@@ -132,6 +174,21 @@ extern "C" int vb_sgd_momentum_clip_step(const void* chunk_table, int32_t n_chun
     sgd_momentum_clip_kernel<<<n_chunks, OPT_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(
         static_cast<const OptChunk*>(chunk_table), grad_arena, momentum_arena, sumsq_partials, n_partials, grad_norm_out, max_norm, lr,
         momentum, weight_decay, first_step);
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+extern "C" int vb_adamw_clip_step(const void* chunk_table, int32_t n_chunks, const float* grad_arena, float* exp_avg_arena,
+                                  float* exp_avg_sq_arena, const float* sumsq_partials, int32_t n_partials, float* grad_norm_out,
+                                  float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                  float bias_correction1, float bias_correction2, vb_stream_t stream_) {
+    using namespace vb;
+    VB_CHECK_ARG(chunk_table && grad_arena && exp_avg_arena && exp_avg_sq_arena && sumsq_partials && n_chunks > 0 && n_partials > 0,
+                 "vb_adamw_clip_step: bad args");
+    VB_CHECK_ARG(bias_correction1 > 0.f && bias_correction2 > 0.f, "vb_adamw_clip_step: bias corrections must be > 0");
+    adamw_clip_kernel<<<n_chunks, OPT_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<const OptChunk*>(chunk_table), grad_arena, exp_avg_arena, exp_avg_sq_arena, sumsq_partials, n_partials, grad_norm_out,
+        max_norm, lr, beta1, beta2, eps, weight_decay, lr / bias_correction1, 1.f / sqrtf(bias_correction2));
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
