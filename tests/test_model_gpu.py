@@ -418,3 +418,48 @@ def test_no_cpu_fallback():
                          "cls_token": True, "output_type": "classification", "n_classes": 3}, device="cpu")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(torch.zeros(1, 3, 32, 32))
+
+
+@pytest.mark.parametrize("opt_name", ["sgd", "adamw"])
+def test_checkpoint_round_trip_like_reference_checkpointer(opt_name, tmp_path):
+    """src/vitef/monitor/checkpoint.py:208-237: ``get_state_dict(model, optimizers)`` -> ``dcp.save`` -> ``dcp.load`` ->
+    ``set_state_dict`` on the drop-in modules with the fused arena optimizers: parameters, moment buffers and step count
+    come back, and the next step of the restored pair equals the next step of the original."""
+    import torch.distributed.checkpoint as dcp
+    from torch.distributed.checkpoint.state_dict import get_state_dict, set_state_dict
+
+    from vit_plasticity_b200.finetune import build_optimizer, train_step
+
+    gold = load("tiny")
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    xs = [O.synthetic_images(4, arch, 70 + i).to(DEV) for i in range(3)]
+    ys = [O.synthetic_labels(4, arch, 80 + i).to(DEV) for i in range(3)]
+
+    def make():
+        m = build("tiny", gold, arch, sd)
+        m.train()
+        kw = dict(lr=1e-2, momentum=0.9) if opt_name == "sgd" else dict(lr=1e-3, weight_decay=1e-2)
+        return m, build_optimizer(m, opt_name, fused=True, **kw)
+
+    model, opt = make()
+    for i in range(2):
+        train_step(model, opt, [(xs[i], ys[i])], grad_clip=1.0)
+    model_sd, optim_sd = get_state_dict(model=model, optimizers=opt)
+    dcp.save({"model": model_sd, "optim": optim_sd}, checkpoint_id=str(tmp_path / "ckpt"))
+
+    model2, opt2 = make()
+    m2, o2 = get_state_dict(model=model2, optimizers=opt2)
+    state = {"model": m2, "optim": o2}
+    dcp.load(state, checkpoint_id=str(tmp_path / "ckpt"))
+    set_state_dict(model=model2, optimizers=opt2, model_state_dict=state["model"], optim_state_dict=state["optim"])
+    assert opt2._steps == opt._steps == 2
+    for (k, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+        assert torch.equal(a, b), k
+    for name in ("momentum_arena", "exp_avg", "exp_avg_sq"):
+        if getattr(opt, name, None) is not None:
+            assert torch.equal(getattr(opt, name), getattr(opt2, name)), name
+    out = [train_step(m, o, [(xs[2], ys[2])], grad_clip=1.0) for m, o in ((model, opt), (model2, opt2))]
+    assert abs(float(out[0][0]) - float(out[1][0])) <= 1e-5
+    for (k, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+        assert rel_l2(b, a) <= 1e-5, (k, rel_l2(b, a))

@@ -135,7 +135,38 @@ class FusedSGD(torch.optim.Optimizer):
         self.partials = torch.zeros(1024, device=dev, dtype=torch.float32)  # per-block sums of squares (fixed-order reduction)
         self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self._steps = 0
+        self._register_state()
         self.zero_grad()
+
+    def _arena_view(self, arena, p):
+        off = self.offset[p]
+        return arena[off : off + p.numel()].view_as(p)
+
+    def _state_arenas(self) -> dict:
+        """state-dict key -> arena, in torch.optim.SGD's vocabulary, so checkpoints interchange with the unfused optimizer"""
+        return {"momentum_buffer": self.momentum_arena} if self.momentum_arena is not None else {}
+
+    def _register_state(self) -> None:
+        """Expose the arenas through ``self.state`` as per-parameter views (what ``state_dict()`` / the reference's
+        ``Checkpointer`` — ``torch.distributed.checkpoint.state_dict.get_state_dict`` — serialise)."""
+        for p in self.trainable:
+            for key, arena in self._state_arenas().items():
+                self.state[p][key] = self._arena_view(arena, p)
+        self.param_groups[0]["fused_steps"] = self._steps
+
+    def load_state_dict(self, state_dict) -> None:
+        """Loaded tensors are copied INTO the arenas (torch would otherwise re-point ``self.state`` at fresh tensors the
+        kernels never read); the step count (first-step momentum initialisation, Adam bias correction) comes back too."""
+        super().load_state_dict(state_dict)
+        for p in self.trainable:
+            st = self.state.get(p, {})
+            for key, arena in self._state_arenas().items():
+                view = self._arena_view(arena, p)
+                loaded = st.get(key)
+                if loaded is not None and loaded.data_ptr() != view.data_ptr():
+                    view.copy_(loaded)
+                self.state[p][key] = view
+        self._steps = int(self.param_groups[0].get("fused_steps", 0))
 
     def _slot(self, p):
         off = self.offset[p]
@@ -167,6 +198,7 @@ class FusedSGD(torch.optim.Optimizer):
         L.sumsq_partials_f32(self.arena, self.partials)
         self._update(float("inf") if max_norm is None else max_norm)
         self._steps += 1
+        self.param_groups[0]["fused_steps"] = self._steps
         for p in self.trainable:  # the kernel wrote through raw pointers: let version-keyed caches (bf16 shadows) see it
             torch.autograd.graph.increment_version(p)
         return self.grad_norm[0]
@@ -190,6 +222,12 @@ class FusedAdamW(FusedSGD):
         self.param_groups[0].update(betas=tuple(betas), eps=eps)
         self.exp_avg = torch.zeros_like(self.arena)
         self.exp_avg_sq = torch.zeros_like(self.arena)
+        self._register_state()
+
+    def _state_arenas(self) -> dict:
+        if not hasattr(self, "exp_avg"):  # (called once from the base constructor, before the moment arenas exist)
+            return {}
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
 
     def _update(self, max_norm: float) -> None:
         from . import _lib as L
