@@ -151,6 +151,15 @@ int vb_attention_pair_delta(const void* qkv_a, const void* qkv_b, int64_t ld_qkv
 int vb_attention_pair_delta_layers(const void* qkv_a, const void* qkv_b, int64_t ld_qkv, void* delta, int32_t layers,
                                    int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
 
+/* Perturbation form of the paired attention (apps/vit/analysis.py:216-233 evaluated on a pair (x, x + dx);
+ * apps/plots/loss_landscape.py:180-191 style magnitude sweeps): qkv_a = W t_a + b are the projections of the base tokens,
+ * dqkv = W (t_b - t_a) those of the token DIFFERENCE (no bias), same layout as above. Writes
+ * delta = attn(t_b) - attn(t_a), bf16 [layers, batch*seq, E], with the score difference, the probability difference and
+ * the output difference each formed from the small operands directly (never as a difference of two rounded
+ * forward passes), so the relative accuracy does not depend on |t_b - t_a| / |t_a|. seq <= 208, head_dim 64. */
+int vb_attention_perturb_delta_layers(const void* qkv_a, const void* dqkv, int64_t ld_qkv, void* delta, int32_t layers,
+                                      int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / data-movement helpers on the path
  * ------------------------------------------------------------------------------------------------ */
@@ -209,6 +218,19 @@ int vb_rowsumsq_diff_f32(const float* a, const float* b, float* out, int32_t n_s
  * (LN_i(a) - LN_i(b) = gamma_i * (zhat_a - zhat_b); beta cancels). a, b: f32 [n_samples*rows, cols]. */
 int vb_layernorm_pair_sqdiff(const float* a, const float* b, float* u, int32_t n_samples, int32_t rows_per_sample,
                              int32_t cols, float eps, vb_stream_t stream);
+
+/* Perturbation form of vb_layernorm_pair_sqdiff: the second input is b = a + scale * d (d: f32 token difference);
+ * zhat_b - zhat_a is evaluated without cancellation (see layernorm.cu), d = 0 gives exactly 0. */
+int vb_layernorm_delta_sqdiff(const float* a, const float* d, float scale, float* u, int32_t n_samples,
+                              int32_t rows_per_sample, int32_t cols, float eps, vb_stream_t stream);
+/* dst = bf16(scale * src), n bf16 elements (the sweep re-uses the unit-noise projections for every magnitude). */
+int vb_scale_bf16(const void* src, void* dst, int64_t n, float scale, vb_stream_t stream);
+/* Perturbation directions of the sweep, generated on the device: out f32 [n_images, elems_per_image] standard normals
+ * from Philox4x32-10 keyed by `seed` with the image index (first_image + row) in the counter, so an image's noise does not
+ * depend on batching or sharding. Replaces the host-side torch.randn of the reference-style sweep
+ * (apps/plots/loss_landscape.py:172-191). Integer stream and transform: oracle/philox_oracle.py. */
+int vb_philox_normal_f32(float* out, int64_t n_images, int64_t elems_per_image, uint64_t seed, uint64_t first_image,
+                         vb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused optimizer step on a flat gradient arena (apps/vit/train.py:277-283: clip_grad_norm_ + optimizer.step with

@@ -98,6 +98,55 @@ def test_two_rank_gloo_matches_single_process(bucket_mb, freeze_first, overlap, 
         assert n_buckets >= (2 if bucket_mb < 1 else 1)
 
 
+def _acc_worker(rank, world, port, outdir, overlap):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from vit_plasticity_b200.distributed import DataParallel
+    from vit_plasticity_b200.finetune import train_step
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _make_model()
+        dp = DataParallel(model, bucket_mb=0.002, overlap=overlap)
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(16, 16, generator=g), torch.randint(0, 4, (16,), generator=g)
+        opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
+        for step in range(2):
+            lo = step * 8 + rank * 4  # this rank's 4 samples of the step's 8, as two micro-batches of 2
+            batches = [(x[lo : lo + 2], y[lo : lo + 2]), (x[lo + 2 : lo + 4], y[lo + 2 : lo + 4])]
+            train_step(dp, opt, batches, grad_clip=1.0, after_backward=dp.finish_grad_sync)
+        torch.save({k: v.clone() for k, v in model.state_dict().items()}, os.path.join(outdir, f"acc{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_two_rank_gradient_accumulation_matches_single_process(overlap, tmp_path):
+    """grad_acc_steps = 2 under data parallelism (apps/vit/train.py:263-270 accumulates micro-batches before the step): only
+    the last micro-batch's backward may launch the bucket all-reduces; replicas stay identical and equal the
+    single-process step on the concatenated batch (equal micro-batch sizes: mean of means)."""
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_acc_worker, args=(r, 2, port, str(tmp_path), overlap)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    sds = [torch.load(tmp_path / f"acc{r}.pt", weights_only=False) for r in range(2)]
+    model = _make_model()
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(16, 16, generator=g), torch.randint(0, 4, (16,), generator=g)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
+    for step in range(2):
+        torch.nn.functional.cross_entropy(model(x[step * 8 : step * 8 + 8]), y[step * 8 : step * 8 + 8]).backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+    for k, v in model.state_dict().items():
+        assert torch.equal(sds[0][k], sds[1][k]), f"replicas differ in {k}"
+        assert torch.allclose(sds[0][k], v, atol=1e-6), k
+
+
 def test_shard_range_partitions_units():
     from vit_plasticity_b200.distributed import shard_range
 
@@ -124,7 +173,7 @@ def test_env_contract_without_torchrun(monkeypatch):
         D.build_manager({"device": "cpu", "tp": 2, "dp": 1})
 
 
-def _gather_worker(rank, world, port, outdir):
+def _gather_worker(rank, world, port, outdir, n_total):
     import numpy as np
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
@@ -132,24 +181,27 @@ def _gather_worker(rank, world, port, outdir):
     from vit_plasticity_b200.distributed import shard_range
     from vit_plasticity_b200.plasticity import gather_tables
 
-    n_total, rows = 11, 4
+    n_eps, rows = 2, 4
     lo, hi = shard_range(n_total, rank, world)
-    # column j of the full table holds j in every row: the gathered table must be 0..n_total-1 in order
-    local = np.tile(np.arange(lo, hi, dtype=np.float32), (rows, 1))
-    table = gather_tables(local, n_total)
+    # column j of the full table holds j (+ 100 * eps index) in every row: the gathered table must be 0..n_total-1 in order
+    local = torch.arange(lo, hi, dtype=torch.float32).expand(n_eps, rows, hi - lo) + 100.0 * torch.arange(n_eps).view(n_eps, 1, 1)
+    table = gather_tables(local.contiguous(), n_total, (n_total + world - 1) // world)
     if rank == 0:
-        np.save(os.path.join(outdir, "table.npy"), table)
+        np.save(os.path.join(outdir, "table.npy"), table.numpy())
     else:
         assert table is None
     dist.destroy_process_group()
 
 
-def test_sweep_gather_reassembles_shards_in_order(tmp_path):
-    """The sweep's only collective: rank-ordered contiguous shards come back as one table on rank 0."""
+@pytest.mark.parametrize("world,n_total", [(2, 11), (3, 4), (2, 1)])
+def test_sweep_gather_reassembles_shards_in_order(tmp_path, world, n_total):
+    """The sweep's only collective: rank-ordered contiguous shards (ragged, possibly empty tail shards, every rank padded
+    to the common shard size) come back as one [n_eps, rows, n_total] table on rank 0."""
     import numpy as np
 
     port = _free_port()
-    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_gather_worker, args=(world, port, str(tmp_path), n_total), nprocs=world, join=True)
     table = np.load(tmp_path / "table.npy")
-    assert table.shape == (4, 11)
-    assert (table == np.arange(11, dtype=np.float32)).all()
+    assert table.shape == (2, 4, n_total)
+    for e in range(2):
+        assert (table[e] == np.arange(n_total, dtype=np.float32) + 100.0 * e).all()

@@ -414,6 +414,61 @@ def test_attention_pair_delta_all_layers(layers, batch, seq, heads):
     assert float(zero.float().abs().max()) == 0.0
 
 
+def _attn_core64(qkv, batch, seq, heads, hd):
+    """fp64 attention core of a [batch*seq, 3E] projection tensor -> [batch*seq, E]"""
+    e = heads * hd
+    q, k, v = (t.reshape(batch, seq, heads, hd).transpose(1, 2) for t in qkv.double().split(e, dim=1))
+    o = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1) @ v
+    return o.transpose(1, 2).reshape(batch * seq, e)
+
+
+@pytest.mark.parametrize("layers,batch,seq,heads", [(3, 5, 197, 12), (2, 3, 5, 2), (1, 150, 197, 4), (2, 2, 208, 3), (1, 4, 130, 2)])
+@pytest.mark.parametrize("scale", [10.0, 1.0, 1e-2, 1e-4])
+def test_attention_perturb_delta_all_layers(layers, batch, seq, heads, scale):
+    """Perturbation-form paired attention: attn(a + d) - attn(a) from (qkv_a, dqkv), against fp64 on the SAME bf16
+    operands. Stated tolerance: relative L2 error of every layer's [tokens, E] difference <= 1e-2 at every
+    perturbation size (bf16 roundings of p, g and the output only; no cancellation), exactly 0 for d = 0."""
+    L = _lib()
+    hd = 64
+    e = heads * hd
+    qa = _rand(batch * seq, layers * 3 * e, seed=1).bfloat16()
+    dq = (_rand(batch * seq, layers * 3 * e, seed=2) * scale).bfloat16()
+    delta = L.attention_perturb_delta_layers(qa, dq, layers, batch, seq, heads, hd)
+    torch.cuda.synchronize()
+    assert delta.shape == (layers, batch * seq, e)
+    assert torch.isfinite(delta.float()).all()
+    for i in range(layers):
+        sl = slice(i * 3 * e, (i + 1) * 3 * e)
+        ref = _attn_core64(qa[:, sl].double() + dq[:, sl].double(), batch, seq, heads, hd) - _attn_core64(qa[:, sl], batch, seq, heads, hd)
+        err = float((delta[i].double() - ref).norm() / ref.norm())
+        assert err <= 1e-2, f"layer {i} scale {scale}: rel L2 {err:.3e}"
+        # row-wise too: no token may be off by more than 3 % of its own difference norm (bf16 output rounding is 0.4 %).
+        # scale 10 on unit-variance projections is far outside the estimator's regime (score differences of ~100 nats: the
+        # perturbed softmax is one-hot on a key that had negligible weight before, lb << la, and the bf16 roundings of p and
+        # g stop cancelling in GQ - (dl / la) Na): measured worst row 4.9e-2, held to 1e-1 there
+        rerr = (delta[i].double() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-30)
+        row_tol = 1e-1 if scale >= 10 else 3e-2
+        assert float(rerr.max()) <= row_tol, f"layer {i} scale {scale}: worst row rel {float(rerr.max()):.3e} at row {int(rerr.argmax())}"
+    zero = L.attention_perturb_delta_layers(qa, torch.zeros_like(dq), layers, batch, seq, heads, hd)
+    torch.cuda.synchronize()
+    assert float(zero.float().abs().max()) == 0.0
+
+
+def test_attention_perturb_delta_large_score_shift_is_finite():
+    """A difference whose scores exceed the fp32 exp range (|dS| / 8 >> 88) must not produce inf / nan: the row max of dS
+    is removed before the exponential."""
+    L = _lib()
+    layers, batch, seq, heads, hd = 1, 2, 197, 2, 64
+    e = heads * hd
+    qa = _rand(batch * seq, 3 * e, seed=3).bfloat16()
+    dq = (_rand(batch * seq, 3 * e, seed=4) * 40.0).bfloat16()
+    delta = L.attention_perturb_delta_layers(qa, dq, layers, batch, seq, heads, hd)
+    torch.cuda.synchronize()
+    assert torch.isfinite(delta.float()).all()
+    ref = _attn_core64(qa.double() + dq.double(), batch, seq, heads, hd) - _attn_core64(qa, batch, seq, heads, hd)
+    assert float((delta[0].double() - ref).norm() / ref.norm()) <= 2e-2
+
+
 # ---------------------------------------------------------------------------------------------------
 # Element-wise helpers
 # ---------------------------------------------------------------------------------------------------
@@ -513,3 +568,48 @@ def test_fused_arena_optimizers_match_torch(opt_name):
         assert abs(float(n_ref) - float(n_got)) <= 1e-5 * float(n_ref)
         for p, q in zip(ref, got):
             _report(f"{opt_name} step {step}", q.detach().reshape(1, -1), p.detach().reshape(1, -1), atol=2e-6, rtol=2e-5)
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-3, 1e-6, 30.0])
+@pytest.mark.parametrize("cols", [128, 768, 1024])
+def test_layernorm_delta_sqdiff(scale, cols):
+    """u[s, c] = sum_rows (zhat(a + scale d) - zhat(a))^2 in perturbation form against fp64; stated tolerance 2e-5
+    relative at every scale (two fp32 LayerNorms subtracted lose ~1e-7 / scale), exactly 0 for d = 0."""
+    L = _lib()
+    s, rows = 3, 197
+    a = _rand(s * rows, cols, seed=1)
+    d = _rand(s * rows, cols, seed=2)
+    u = torch.zeros(s, cols, device=DEV)
+    L.layernorm_delta_sqdiff(a, d, scale, u, s, rows, cols, 1e-12)
+    za = torch.nn.functional.layer_norm(a.double(), (cols,), eps=1e-12)
+    zb = torch.nn.functional.layer_norm(a.double() + scale * d.double(), (cols,), eps=1e-12)
+    ref = ((zb - za) ** 2).reshape(s, rows, cols).sum(1)
+    assert float(((u.double() - ref).abs() / ref).max()) <= 2e-5
+    u0 = torch.zeros(s, cols, device=DEV)
+    L.layernorm_delta_sqdiff(a, torch.zeros_like(d), 1.0, u0, s, rows, cols, 1e-12)
+    assert float(u0.abs().max()) == 0.0
+
+
+def test_scale_bf16():
+    L = _lib()
+    x = _rand(1000, 1237, seed=5).bfloat16().reshape(-1)[: 1000 * 1237 - 3].contiguous()  # ragged tail
+    y = L.scale_bf16(x, 1e-3)
+    assert torch.equal(y, (x.float() * 1e-3).bfloat16())
+
+
+def test_philox_normal_matches_oracle_and_is_batching_invariant():
+    """Device noise generator of the sweep against oracle/philox_oracle.py (Philox4x32-10 pinned on Random123's known
+    answers; Box-Muller in fp64 there, fp32 here: abs tolerance 2e-5), and image i's noise is the same whatever batch or
+    shard it is drawn in."""
+    from oracle.philox_oracle import normal_images
+
+    L = _lib()
+    shape, seed = (3, 32, 32), 5
+    got = L.philox_normal(6, shape, seed, 7, DEV)
+    ref = torch.from_numpy(normal_images(6, 3 * 32 * 32, seed, 7)).reshape(6, *shape)
+    assert float((got.cpu() - ref).abs().max()) <= 2e-5
+    again = torch.cat([L.philox_normal(2, shape, seed, 7, DEV), L.philox_normal(4, shape, seed, 9, DEV)])
+    assert torch.equal(got, again)
+    big = L.philox_normal(64, (3, 224, 224), 1, 2**33, DEV)  # image indices beyond 32 bits reach the counter's high word
+    assert abs(float(big.mean())) < 2e-3 and abs(float(big.std()) - 1.0) < 2e-3 and torch.isfinite(big).all()
+    assert not torch.equal(big[0], L.philox_normal(1, (3, 224, 224), 1, 0, DEV)[0])

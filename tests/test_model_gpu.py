@@ -9,7 +9,13 @@ Stated tolerances (bf16 storage / fp32 accumulate vs the reference's fp32):
                 total grad-norm within 2e-2 relative. The ViT-B/16 fixture holds 256 strided samples + the norm per
                 tensor: that sampled estimate of the same relative error has ~±15 % estimator noise on top of the
                 2-3.5 % bf16 error of the deepest fc1 / qkv weights, so it is held to 6e-2.
-  plasticity    independent pairs: ratios within 2e-2 relative (attention), 5e-3 (LayerNorm / fc1 / fc2)
+                Where the fixture also holds a "slab" (the first 4096 contiguous elements of a large gradient, stored
+                verbatim), the relative L2 error over the slab is held to 5e-2 (ViT-B/16, ViT-L/16).
+  plasticity    ratios to the embedding distance within 5e-3 relative (attention), 1e-3 (LayerNorm / fc1 / fc2), for
+                independent pairs AND for perturbation pairs (x, x + eps n) at every eps of the fixture grid
+                {10, 1, 1e-1, 1e-2, 1e-3} — the estimator carries (x, d), so its accuracy does not depend on eps. The
+                fixtures are the reference's fp32 outputs, whose own round-off is <= 2e-4 at eps = 1e-3 (the fixture
+                also holds the same reference modules run in float64 to tell the two apart; reported, not asserted).
 """
 
 import json
@@ -26,6 +32,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).parent / "golden"
 DEV = "cuda"
 REPORT = {}
+VIT_NAMES = ("vit_base", "vit_large")  # fixtures built through the ViT wrapper (state_dict keys carry "model.")
 
 
 def _dump_report():
@@ -55,8 +62,8 @@ def rel_l2(got, ref):
 def build(name, gold, arch, sd):
     from vit_plasticity_b200 import build_model
 
-    if name == "vit_base":
-        cfg = dict(implementation="vit", model_name="base", pretrained=False, in21k=True, finetuning=True, n_classes=arch.n_classes)
+    if name in VIT_NAMES:
+        cfg = dict(implementation="vit", model_name=name.split("_")[1], pretrained=False, in21k=True, finetuning=True, n_classes=arch.n_classes)
         model = build_model(cfg, device=DEV)
         model.load_state_dict({"model." + k: v for k, v in sd.items()})
     else:
@@ -82,12 +89,17 @@ def check_summary(got, summ, tol, what):
         err = float((sample.double() - summ["sample"].double()).norm() / (256**0.5 * rms + 1e-30))
         nerr = abs(float(got.double().norm()) - summ["norm"]) / (summ["norm"] + 1e-30)
         err = max(err, nerr)
+        if "slab" in summ:  # whole leading rows stored verbatim: a real relative L2 error, not a sampled estimate
+            slab = summ["slab"]
+            serr = rel_l2(got.flatten()[: slab.numel()], slab)
+            REPORT.setdefault("grad_slab_rel_l2", {})[what] = serr
+            assert serr <= 5e-2, f"{what}: slab relative L2 error {serr:.3e} > 5e-2"
     REPORT.setdefault("grad_rel_l2", {})[what] = err
     assert err <= tol, f"{what}: relative error {err:.3e} > {tol}"
     return err
 
 
-@pytest.mark.parametrize("name", ["tiny", "small", "vit_base"])
+@pytest.mark.parametrize("name", ["tiny", "small", "vit_base", "vit_large"])
 def test_logits_loss_grads_match_reference(name):
     from vit_plasticity_b200.finetune import freeze_model
 
@@ -98,7 +110,7 @@ def test_logits_loss_grads_match_reference(name):
     x = O.synthetic_images(gold["batch"], arch, gold["x_seed"]).to(DEV)
     y = O.synthetic_labels(gold["batch"], arch, gold["y_seed"]).to(DEV)
     model.train()
-    prefix = "model." if name == "vit_base" else ""
+    prefix = "model." if name in VIT_NAMES else ""
     for fs, ref in gold["train"].items():
         for p in model.parameters():
             p.requires_grad_(True)
@@ -146,7 +158,7 @@ def test_against_cpu_oracle_same_inputs(name):
     loss.backward()
     assert rel_l2(logits, o_logits) <= 2e-2
     assert abs(float(loss) - float(o_loss)) <= 2e-2
-    prefix = "model." if name == "vit_base" else ""
+    prefix = "model." if name in VIT_NAMES else ""
     errs = {k: rel_l2(p.grad, o_grads[k[len(prefix):]]) for k, p in model.named_parameters()}
     REPORT[f"{name}/oracle_full_tensor"] = {"worst_grad_rel_l2": max(errs.values()), "worst_tensor": max(errs, key=errs.get),
                                             "logits_rel_l2": rel_l2(logits, o_logits)}
@@ -163,7 +175,7 @@ def test_train_step_matches_reference(name):
     arch = arch_of(gold)
     sd = O.init_state_dict(arch, seed=gold["weights_seed"])
     model = build(name, gold, arch, sd)
-    prefix = "model." if name == "vit_base" else ""
+    prefix = "model." if name in VIT_NAMES else ""
     ref = gold["train"]["full"]
     x = O.synthetic_images(gold["batch"], arch, gold["x_seed"]).to(DEV)
     y = O.synthetic_labels(gold["batch"], arch, gold["y_seed"]).to(DEV)
@@ -244,7 +256,7 @@ def test_fused_sgd_train_step_matches_reference_fixture():
     _dump_report()
 
 
-@pytest.mark.parametrize("name", ["tiny", "small", "vit_base"])
+@pytest.mark.parametrize("name", ["tiny", "small", "vit_base", "vit_large"])
 def test_plasticity_matches_reference(name):
     from vit_plasticity_b200.plasticity import PlasticityEstimator, get_plasticity
 
@@ -265,7 +277,7 @@ def test_plasticity_matches_reference(name):
         worst[comp] = max(worst.get(comp, 0.0), err)
     ratios = get_plasticity(dist)
     for comp, per_layer in ratios.items():
-        tol = 2e-2 if comp == "attn" else 5e-3
+        tol = 5e-3 if comp == "attn" else 1e-3
         for i, r in enumerate(per_layer):
             ref = p["ratios"][f"block{i}_{comp}"].numpy()
             err = float(np.max(np.abs(r - ref) / ref))
@@ -276,26 +288,34 @@ def test_plasticity_matches_reference(name):
     same = est.pair_distances(x1, x1)
     nonzero = {k: float(np.abs(v).max()) for k, v in same.items() if float(np.abs(v).max()) != 0.0}
     assert not nonzero, f"identical inputs must give exactly zero distances, got {nonzero}"
-    swapped = est.pair_distances(x2, x1)
+    swapped = est.pair_distances(x2, x1)  # the pair is carried as (base, difference): swapping changes the base point
     for k in dist:
-        assert np.allclose(swapped[k], dist[k], rtol=2e-3), k
-    # small perturbations: x' = x + eps * noise (fixture holds the fp32 reference ratios)
+        assert np.allclose(swapped[k], dist[k], rtol=5e-3 if k.endswith("_attn") else 1e-3), k
+    # perturbation pairs x' = x + eps * noise over the whole grid (fixture: the fp32 reference's ratios)
     noise = O.synthetic_images(p["n_pairs"], arch, gold["plasticity_eps_noise_seed"]).to(DEV)
     for eps, ref_r in gold["plasticity_eps"].items():
         d = est.pair_distances(x1, x1 + eps * noise)
-        errs = {}
+        errs, errs64 = {}, {}
         for k, r in ref_r.items():
             comp = k.split("_", 1)[1]
-            errs[comp] = max(errs.get(comp, 0.0), float(np.max(np.abs(d[k] / d["embedding"] - r.numpy()) / r.numpy())))
+            got = d[k] / d["embedding"]
+            errs[comp] = max(errs.get(comp, 0.0), float(np.max(np.abs(got - r.numpy()) / r.numpy())))
+            r64 = gold["plasticity_eps_f64"][eps][k].numpy()
+            errs64[comp] = max(errs64.get(comp, 0.0), float(np.max(np.abs(got - r64) / r64)))
         REPORT[f"{name}/plasticity_eps_{eps}"] = errs
-        for comp in ("ffn_fc1", "ffn_fc2"):  # linear components run on the fp32 difference: eps-independent accuracy
-            assert errs[comp] <= 5e-3, f"{name}: eps={eps} {comp} rel err {errs[comp]:.3e}"
+        REPORT[f"{name}/plasticity_eps_{eps}_vs_f64_reference"] = errs64
+        for comp, err in errs.items():
+            tol = 5e-3 if comp == "attn" else 1e-3  # measured worst: 3.6e-3 / 6.8e-4 (tiny); ViT-B/L: 3.9e-4 / 3.6e-5
+            assert err <= tol, f"{name}: eps={eps} {comp} rel err {err:.3e} > {tol}"
     _dump_report()
 
 
 def test_perturbation_sweep_matches_oracle_and_is_shard_invariant():
-    """configs[4] driver on one GPU: ratios against the CPU oracle on the same (x, x + eps n) pairs; running the two
-    halves as the two ranks of a world-size-2 job gives the same table (noise is per image, shards are contiguous)."""
+    """configs[4] driver on one GPU: ratios against the CPU oracle on the same (x, x + eps n) pairs over a log grid down to
+    1e-3 (n from the device generator, reproduced on the host by oracle/philox_oracle.py); running the two halves as the
+    two ranks of a world-size-2 job gives the same table (noise is keyed by image index, shards are contiguous)."""
+    from oracle.philox_oracle import normal_images
+
     from vit_plasticity_b200.plasticity import PlasticityEstimator, perturbation_sweep
 
     gold = load("small")
@@ -304,24 +324,32 @@ def test_perturbation_sweep_matches_oracle_and_is_shard_invariant():
     model = build("small", gold, arch, sd).eval()
     n = 6
     x = O.synthetic_images(n, arch, 31)
-    eps_list = [1.0, 0.1]
+    eps_list = [10.0, 1.0, 0.1, 1e-2, 1e-3]
     full = perturbation_sweep(model, x, eps_list, noise_seed=5, pairs_per_call=4)
-    noise = torch.stack([torch.randn(x.shape[1:], generator=torch.Generator().manual_seed(5 * 1_000_003 + i)) for i in range(n)])
+    noise = torch.from_numpy(normal_images(n, x[0].numel(), 5, 0)).reshape(x.shape)
+    sd64 = {k: v.double() for k, v in sd.items()}
     for eps in eps_list:
-        ref = O.pair_distances(sd, x, x + eps * noise, arch)
+        # float64 oracle: at eps = 1e-3 the fp32 oracle's own round-off (~2e-4) would eat into the tolerance
+        ref = O.pair_distances(sd64, x.double(), x.double() + eps * noise.double(), arch)
+        worst = {}
         for k, v in ref.items():
             if k == "embedding":
                 continue
             r_ref = v / ref["embedding"]
             r = full[eps][k] / full[eps]["embedding"]
-            tol = 5e-2 if "attn" in k.split("_", 1)[1] or "norm" in k else 5e-3  # non-linear components lose digits as eps shrinks
-            assert np.max(np.abs(r - r_ref) / r_ref) <= tol, (eps, k, float(np.max(np.abs(r - r_ref) / r_ref)))
+            comp = k.split("_", 1)[1]
+            worst[comp] = max(worst.get(comp, 0.0), float(np.max(np.abs(r - r_ref) / r_ref)))
+        REPORT[f"small/sweep_eps_{eps}"] = worst
+        for comp, err in worst.items():
+            tol = 5e-3 if comp == "attn" else 1e-3
+            assert err <= tol, (eps, comp, err)
     est = PlasticityEstimator(model)
     halves = [perturbation_sweep(model, x, eps_list, noise_seed=5, pairs_per_call=4, rank=r, world=2, estimator=est) for r in range(2)]
     for eps in eps_list:
         for k in full[eps]:
             both = np.concatenate([halves[0][eps][k], halves[1][eps][k]])
             assert np.allclose(both, full[eps][k], rtol=1e-5, atol=0), (eps, k)
+    _dump_report()
 
 
 def test_analysis_loop_writes_reference_distances_pkl(tmp_path):

@@ -73,6 +73,21 @@ def test_vit_base_schema_and_param_counts():
     assert arch.seq_len == 197
 
 
+def test_vit_large_schema_and_param_counts():
+    """BASELINE.json configs[3] / [4]: the ViT-L/16 fixture was produced by the reference's own ViT wrapper."""
+    gold = load("vit_large")
+    arch = arch_of(gold)
+    assert (arch.emb_dim, arch.n_heads, arch.n_layers, arch.ffn_dim) == (1024, 16, 24, 4096)  # src/vitef/models/vit.py:130-134
+    assert gold["n_params"] == 303_311_882  # SURVEY.md section 8(a) row a10
+    assert len(gold["state_dict_keys"]) == 296 and all(k.startswith("model.") for k in gold["state_dict_keys"])
+    assert gold["train"]["attention_only"]["n_trainable"] == 100_773_898
+    assert gold["train"]["mlp_only"]["n_trainable"] == 201_461_770
+    assert len(gold["plasticity"]["keys"]) == 1 + 5 * 24
+    assert sorted(gold["plasticity_eps"]) == [1e-3, 1e-2, 1e-1, 1.0, 10.0]
+    # the fixture holds whole leading rows ("slab") of every large gradient of the full-finetuning step
+    assert "slab" in gold["train"]["full"]["grads"]["blocks.23.ffn.fc1.weight"]
+
+
 @pytest.mark.parametrize("name", ["tiny", "small"])
 def test_forward_and_train_step(name):
     gold = load(name)

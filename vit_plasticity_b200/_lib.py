@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint64, c_void_p
 from pathlib import Path
 
 import torch
@@ -106,6 +106,13 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     ),
+    "vb_attention_perturb_delta_layers": (
+        c_int32,
+        [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    ),
+    "vb_layernorm_delta_sqdiff": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "vb_scale_bf16": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "vb_philox_normal_f32": (c_int32, [c_void_p, c_int64, c_int64, c_uint64, c_uint64, c_void_p]),
     "vb_cast_f32_to_bf16": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vb_cast_bf16_to_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vb_im2col_patches": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
@@ -339,9 +346,43 @@ def attention_pair_delta_layers(qkv_a, qkv_b, layers, batch, seq, heads, head_di
     return delta
 
 
+def attention_perturb_delta_layers(qkv_a, dqkv, layers, batch, seq, heads, head_dim, out=None):
+    """[layers, batch*seq, E] bf16: attn(a + d) - attn(a) for every layer, in perturbation form: ``qkv_a`` holds the
+    projections of the base tokens (with bias), ``dqkv`` those of the token difference (no bias)."""
+    _req(qkv_a, torch.bfloat16, "qkv_a")
+    _req(dqkv, torch.bfloat16, "dqkv")
+    assert qkv_a.stride(0) == dqkv.stride(0) and qkv_a.stride(1) == 1 and dqkv.stride(1) == 1 and qkv_a.shape == dqkv.shape
+    if out is None:
+        out = torch.empty(layers, batch * seq, heads * head_dim, device=qkv_a.device, dtype=torch.bfloat16)
+    _check(
+        lib().vb_attention_perturb_delta_layers(qkv_a.data_ptr(), dqkv.data_ptr(), qkv_a.stride(0), out.data_ptr(), layers, batch, seq, heads, head_dim, _stream()),
+        "vb_attention_perturb_delta_layers",
+    )
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # Element-wise helpers
 # --------------------------------------------------------------------------------------------------
+def scale_bf16(src: torch.Tensor, scale: float, dst: torch.Tensor | None = None) -> torch.Tensor:
+    _req(src, torch.bfloat16, "src")
+    assert src.is_contiguous()
+    if dst is None:
+        dst = torch.empty_like(src)
+    _check(lib().vb_scale_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), float(scale), _stream()), "vb_scale_bf16")
+    return dst
+
+
+def philox_normal(n_images: int, shape, seed: int, first_image: int, device) -> torch.Tensor:
+    """f32 [n_images, *shape] standard normals; row i is the noise of image ``first_image + i`` whatever the batching."""
+    elems = 1
+    for d in shape:
+        elems *= int(d)
+    out = torch.empty(n_images, *shape, device=device, dtype=torch.float32)
+    _check(lib().vb_philox_normal_f32(out.data_ptr(), n_images, elems, int(seed), int(first_image), _stream()), "vb_philox_normal_f32")
+    return out
+
+
 def cast_f32_to_bf16(src: torch.Tensor, dst: torch.Tensor | None = None) -> torch.Tensor:
     _req(src, torch.float32, "src")
     assert src.is_contiguous()
@@ -437,6 +478,13 @@ def rowsumsq_diff_f32(a, b, out, n_samples, rows_per_sample, cols):
 
 def layernorm_pair_sqdiff(a, b, u, n_samples, rows_per_sample, cols, eps):
     _check(lib().vb_layernorm_pair_sqdiff(a.data_ptr(), b.data_ptr(), u.data_ptr(), n_samples, rows_per_sample, cols, float(eps), _stream()), "vb_layernorm_pair_sqdiff")
+
+
+def layernorm_delta_sqdiff(a, d, scale, u, n_samples, rows_per_sample, cols, eps):
+    """u[s, c] += sum_rows (zhat(a + scale d) - zhat(a))^2, evaluated in perturbation form (no cancellation)"""
+    _req(a, torch.float32, "a")
+    _req(d, torch.float32, "d")
+    _check(lib().vb_layernorm_delta_sqdiff(a.data_ptr(), d.data_ptr(), float(scale), u.data_ptr(), n_samples, rows_per_sample, cols, float(eps), _stream()), "vb_layernorm_delta_sqdiff")
 
 
 # --------------------------------------------------------------------------------------------------

@@ -447,6 +447,8 @@ int launch_attention_pair_tc3(const bf16* qkv_a, const bf16* qkv_b, int64_t ld, 
 // Development aid only (never set by the package): VITB200_ATTN=mma forces the mma.sync kernels of this file (the
 // production path for sequences of 209..272 tokens) for every length; default = the persistent tcgen05 kernels of
 // attention_tc3.cu for seq <= 208.
+int launch_attention_delta_tc3(const bf16* qkv_a, const bf16* dqkv, int64_t ld, bf16* delta, int layers, int batch, int L, int H,
+                               cudaStream_t stream);
 static int attn_impl() {
     static int v = -1;
     if (v < 0) {
@@ -509,6 +511,20 @@ extern "C" int vb_attention_pair_delta_layers(const void* qkv_a, const void* qkv
         if (rc) return rc;
     }
     return VB_OK;
+}
+
+extern "C" int vb_attention_perturb_delta_layers(const void* qkv_a, const void* dqkv, int64_t ld_qkv, void* delta, int32_t layers,
+                                                 int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, vb_stream_t stream_) {
+    using namespace vb;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(qkv_a && dqkv && delta, "vb_attention_perturb_delta_layers: null pointer");
+    VB_CHECK_ARG(head_dim == HD, "vb_attention_perturb_delta_layers: head_dim must be 64 (got %d)", head_dim);
+    VB_CHECK_ARG(layers > 0 && batch > 0 && heads > 0 && seq > 0 && seq <= 208, "vb_attention_perturb_delta_layers: seq=%d must be in [1, 208]", seq);
+    const int64_t E = (int64_t)heads * HD;
+    VB_CHECK_ARG(ld_qkv % 8 == 0 && ld_qkv >= layers * 3 * E, "vb_attention_perturb_delta_layers: ld_qkv=%lld must be a multiple of 8, >= layers * 3E",
+                 (long long)ld_qkv);
+    return launch_attention_delta_tc3(static_cast<const bf16*>(qkv_a), static_cast<const bf16*>(dqkv), ld_qkv, static_cast<bf16*>(delta), layers,
+                                      batch, seq, heads, stream);
 }
 
 extern "C" int64_t vb_attention_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads) {

@@ -393,6 +393,328 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
 }
 
 // =====================================================================================================
+// plasticity estimator: attention of a perturbed input, attn(a + d) - attn(a), evaluated in PERTURBATION FORM
+// =====================================================================================================
+// Inputs per (layer, image, head): q, k, v of the base input a (qkv_a = W t_a + b) and dq, dk, dv = W d_tok of the token
+// difference (no bias). Two independent bf16 forward passes lose the difference once |d| << |a| (34-53 % error at a
+// relative perturbation of 1e-2); here every small quantity is its own bf16 tensor with its own exponent:
+//   S   = q k^T                                   (SS MMA, N = 208)              -> buffer A
+//   dS  = q dk^T + dq k^T + dq dk^T  (= S_b - S)  (3 x SS MMA into one accumulator) -> buffer B
+//   p   = exp2((S - rowmax S) c),  l = sum p
+//   g   = p * expm1((dS - rowmax dS) / 8)         (the softmax is shift invariant per row: the row max removes the
+//                                                  common mode of dS; expm1 by a polynomial below 1/8, so p_b - p = g
+//                                                  keeps full relative precision however small dS is)
+//   dl  = sum g,  lb = sum (p + g)                (un-normalised: P_b = (p + g) / lb, P_a = p / l)
+//   Na  = p v,  GQ = g v + g dv + p dv            (TS MMAs: p and g packed to bf16 over buffer A, accumulators over B)
+//   out = O_b - O_a = (GQ - (dl / l) Na) / lb     fp32, one bf16 rounding
+// Exact for any perturbation size (tools/emulate_delta_attention.py: <= 1.2e-3 of the fp64 value from |d|/|a| = 1e-4 to 10).
+// One unit (128 query rows) at a time: TMEM holds S (208) + dS (208) columns, so units are not double-buffered; the
+// Q/K and V operand groups have their own barriers, so the next item's Q/K load overlaps this item's softmax and P V.
+constexpr int D_OFF_QA = 0, D_OFF_KA = OPER_BYTES, D_OFF_DQ = 2 * OPER_BYTES, D_OFF_DK = 3 * OPER_BYTES, D_OFF_VA = 4 * OPER_BYTES,
+              D_OFF_DV = 5 * OPER_BYTES;
+constexpr int D_EXCH_FLOATS = 4 * 128;  // one value per (column part, row)
+constexpr int D_SMEM = 6 * OPER_BYTES + 5 * D_EXCH_FLOATS * 4 + 256 + 1024;
+static_assert(D_SMEM <= 232448, "shared memory budget");
+constexpr uint32_t D_COL_A = 0, D_COL_G = 104, D_COL_B = 208, D_COL_NA = 224, D_COL_GQ = 288;
+
+// exp(w) - 1 for w <= 0: 4th-order polynomial above -1/8 (truncation 3e-7 relative), exp2 - 1 below
+__device__ __forceinline__ float expm1_neg(float w) {
+    const float poly = w * fmaf(w, fmaf(w, fmaf(w, 1.f / 24.f, 1.f / 6.f), 0.5f), 1.f);
+    const float big = fast_ex2(w * LOG2E) - 1.f;
+    return w > -0.125f ? poly : big;
+}
+
+// One row's share of a unit: NC (64 or 48) columns starting at cbeg. Leaves packed bf16 p at buffer-A columns
+// [cbeg / 2, +NC / 2) and packed g at [104 + cbeg / 2, +NC / 2), and the row's partial sums in the exchange arrays.
+template <int NC>
+__device__ __forceinline__ void delta_softmax_part(uint32_t lane_addr, int cbeg, int nvalid, float* sMaxA, float* sMaxW, float* sSumA,
+                                                   float* sSumG, float* sSumB, int part, int row, int quarter) {
+    const float c = 0.125f * LOG2E;
+    uint32_t v0[32], v1[NC - 32];
+    tmem_ld_32x32b_x32(lane_addr + D_COL_A + cbeg, v0);
+    if constexpr (NC == 64)
+        tmem_ld_32x32b_x32(lane_addr + D_COL_A + cbeg + 32, v1);
+    else
+        tmem_ld_32x32b_x16(lane_addr + D_COL_A + cbeg + 32, v1);
+    tmem_ld_wait();
+    reg_fence(v0);
+    reg_fence(v1);
+    float m = -INFINITY, mw = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (i < nvalid) m = fmaxf(m, __uint_as_float(v0[i]));
+#pragma unroll
+    for (int i = 0; i < NC - 32; ++i)
+        if (32 + i < nvalid) m = fmaxf(m, __uint_as_float(v1[i]));
+#pragma unroll
+    for (int pc = 0; pc < NC / 16; ++pc) {
+        uint32_t w[16];
+        tmem_ld_32x32b_x16(lane_addr + D_COL_B + cbeg + pc * 16, w);
+        tmem_ld_wait();
+        reg_fence(w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (pc * 16 + i < nvalid) mw = fmaxf(mw, __uint_as_float(w[i]));
+    }
+    sMaxA[part * 128 + row] = m;
+    sMaxW[part * 128 + row] = mw;
+    named_bar_sync(1 + quarter, 128);  // the four warps sharing this lane quarter: all their S columns are in registers now
+    m = fmaxf(fmaxf(sMaxA[row], sMaxA[128 + row]), fmaxf(sMaxA[256 + row], sMaxA[384 + row]));  // column 0 is valid: finite
+    mw = fmaxf(fmaxf(sMaxW[row], sMaxW[128 + row]), fmaxf(sMaxW[256 + row], sMaxW[384 + row]));
+    const float mc = m * c;
+    // ---- p = exp2((S - m) c), kept in fp32 in the registers that held S; packed bf16 copy -> buffer A ----
+    float la = 0.f;
+    {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float a = (2 * i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v0[2 * i]), c, -mc)) : 0.f;
+            const float b = (2 * i + 1 < nvalid) ? fast_ex2(fmaf(__uint_as_float(v0[2 * i + 1]), c, -mc)) : 0.f;
+            v0[2 * i] = __float_as_uint(a);
+            v0[2 * i + 1] = __float_as_uint(b);
+            pk[i] = pack_bf16x2(a, b);
+            la += a + b;
+        }
+        tmem_st_x16(lane_addr + D_COL_A + (cbeg >> 1), pk);
+    }
+    {
+        uint32_t pk[(NC - 32) / 2];
+#pragma unroll
+        for (int i = 0; i < (NC - 32) / 2; ++i) {
+            const float a = (32 + 2 * i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v1[2 * i]), c, -mc)) : 0.f;
+            const float b = (32 + 2 * i + 1 < nvalid) ? fast_ex2(fmaf(__uint_as_float(v1[2 * i + 1]), c, -mc)) : 0.f;
+            v1[2 * i] = __float_as_uint(a);
+            v1[2 * i + 1] = __float_as_uint(b);
+            pk[i] = pack_bf16x2(a, b);
+            la += a + b;
+        }
+        if constexpr (NC == 64)
+            tmem_st_x16(lane_addr + D_COL_A + (cbeg >> 1) + 16, pk);
+        else
+            tmem_st_x8(lane_addr + D_COL_A + (cbeg >> 1) + 16, pk);
+    }
+    // ---- g = p * expm1((dS - mw) / 8): second pass over the dS columns, 16 at a time ----
+    const float mw8 = mw * 0.125f;
+    float dl = 0.f, lb = 0.f;
+    auto piece = [&](auto& pv, int base, int col) {  // pv[base .. base + 16) hold p of columns [col, col + 16) of this part
+        uint32_t w[16], pk[8];
+        tmem_ld_32x32b_x16(lane_addr + D_COL_B + cbeg + col, w);
+        tmem_ld_wait();
+        reg_fence(w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float p0 = __uint_as_float(pv[base + 2 * i]), p1 = __uint_as_float(pv[base + 2 * i + 1]);
+            // the clamp keeps masked columns (p = 0, dS = 0 there) at expm1(0) = 0 instead of 0 * inf
+            const float g0 = p0 * expm1_neg(fminf(fmaf(__uint_as_float(w[2 * i]), 0.125f, -mw8), 0.f));
+            const float g1 = p1 * expm1_neg(fminf(fmaf(__uint_as_float(w[2 * i + 1]), 0.125f, -mw8), 0.f));
+            pk[i] = pack_bf16x2(g0, g1);
+            dl += g0 + g1;
+            lb += (p0 + g0) + (p1 + g1);
+        }
+        tmem_st_x8(lane_addr + D_COL_G + ((cbeg + col) >> 1), pk);
+    };
+    piece(v0, 0, 0);
+    piece(v0, 16, 16);
+    piece(v1, 0, 32);
+    if constexpr (NC == 64) piece(v1, 16, 48);
+    sSumA[part * 128 + row] = la;
+    sSumG[part * 128 + row] = dl;
+    sSumB[part * 128 + row] = lb;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_perturb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD, bf16* __restrict__ out, int L,
+                       int H, int batch, int n_items) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align_smem(smem_raw);
+    float* sMaxA = reinterpret_cast<float*>(smem + 6 * OPER_BYTES);  // [4][128] each
+    float* sMaxW = sMaxA + D_EXCH_FLOATS;
+    float* sSumA = sMaxW + D_EXCH_FLOATS;
+    float* sSumG = sSumA + D_EXCH_FLOATS;
+    float* sSumB = sSumG + D_EXCH_FLOATS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sSumB + D_EXCH_FLOATS);
+    uint64_t *full_qk = bars, *full_v = bars + 1, *empty_qk = bars + 2, *empty_v = bars + 3, *s_ready = bars + 4, *p_ready = bars + 5,
+             *o_ready = bars + 6, *o_free = bars + 7;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
+    const int E = H * HD;
+    const int n_local = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int U = 2 * n_local;  // units (query tiles) this CTA processes
+
+    if (warp == WARP_TMA && elect_one()) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmD);
+    }
+    if (warp == WARP_MMA) {
+        if (elect_one()) {
+            mbar_init(full_qk, 1);
+            mbar_init(full_v, 1);
+            mbar_init(empty_qk, 1);
+            mbar_init(empty_v, 1);
+            mbar_init(s_ready, 1);
+            mbar_init(p_ready, MATH_WARPS);
+            mbar_init(o_ready, 1);
+            mbar_init(o_free, MATH_WARPS);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == WARP_TMA) {
+        // =========================== TMA producer ===========================
+        for (int n = 0; n < n_local; ++n) {
+            const int it = blockIdx.x + n * gridDim.x;
+            const int hd = it % H, b = (it / H) % batch, layer = it / (H * batch);
+            const int f0 = layer * 3 * E + hd * HD;  // feature of q; k at + E, v at + 2E
+            mbar_wait(empty_qk, (n & 1) ^ 1, 80);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full_qk, 4 * OPER_BYTES);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    tma_load_3d(smem + D_OFF_QA + h2 * BOX_ROWS * 128, &tmA, full_qk, f0, h2 * BOX_ROWS, b);
+                    tma_load_3d(smem + D_OFF_KA + h2 * BOX_ROWS * 128, &tmA, full_qk, f0 + E, h2 * BOX_ROWS, b);
+                    tma_load_3d(smem + D_OFF_DQ + h2 * BOX_ROWS * 128, &tmD, full_qk, f0, h2 * BOX_ROWS, b);
+                    tma_load_3d(smem + D_OFF_DK + h2 * BOX_ROWS * 128, &tmD, full_qk, f0 + E, h2 * BOX_ROWS, b);
+                }
+            }
+            __syncwarp();
+            mbar_wait(empty_v, (n & 1) ^ 1, 81);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full_v, 2 * OPER_BYTES);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    tma_load_3d(smem + D_OFF_VA + h2 * BOX_ROWS * 128, &tmA, full_v, f0 + 2 * E, h2 * BOX_ROWS, b);
+                    tma_load_3d(smem + D_OFF_DV + h2 * BOX_ROWS * 128, &tmD, full_v, f0 + 2 * E, h2 * BOX_ROWS, b);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == WARP_MMA) {
+        // =========================== MMA issuer ===========================
+        const uint32_t idesc_s = make_idesc_bf16(128, ROWS, 0, 0);
+        const uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
+        const uint32_t smem_lo = smem_u32(smem) >> 4;
+        const uint32_t ka = (smem_lo + (D_OFF_KA >> 4)) | LBO_K, dk = (smem_lo + (D_OFF_DK >> 4)) | LBO_K;
+        const uint32_t va = (smem_lo + (D_OFF_VA >> 4)) | LBO_MN, dv = (smem_lo + (D_OFF_DV >> 4)) | LBO_MN;
+        for (int u = 0; u < U; ++u) {
+            const int n = u >> 1, t = u & 1;
+            if (t == 0) mbar_wait(full_qk, n & 1, 82);
+            mbar_wait(o_free, (u & 1) ^ 1, 83);  // the accumulators of unit u-1 (over buffer B) have been read out
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t qa = (smem_lo + ((D_OFF_QA + t * TILE_BYTES) >> 4)) | LBO_K;
+                const uint32_t dq = (smem_lo + ((D_OFF_DQ + t * TILE_BYTES) >> 4)) | LBO_K;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem_base + D_COL_A, make_desc(qa + 2 * k, DESC_HI), make_desc(ka + 2 * k, DESC_HI), idesc_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem_base + D_COL_B, make_desc(qa + 2 * k, DESC_HI), make_desc(dk + 2 * k, DESC_HI), idesc_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem_base + D_COL_B, make_desc(dq + 2 * k, DESC_HI), make_desc(ka + 2 * k, DESC_HI), idesc_s, 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem_base + D_COL_B, make_desc(dq + 2 * k, DESC_HI), make_desc(dk + 2 * k, DESC_HI), idesc_s, 1);
+                umma_commit(s_ready);
+                if (t == 1) umma_commit(empty_qk);  // both query tiles have read Q / K / dQ / dK: the next item may load
+            }
+            __syncwarp();
+            mbar_wait(p_ready, u & 1, 84);
+            if (t == 0) mbar_wait(full_v, n & 1, 85);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 13; ++k)  // 16 keys per step = 8 packed columns
+                    umma_bf16_ts(tmem_base + D_COL_NA, tmem_base + D_COL_A + k * 8, make_desc(va + k * 128, DESC_HI), idesc_o, k > 0);
+#pragma unroll
+                for (int k = 0; k < 13; ++k)
+                    umma_bf16_ts(tmem_base + D_COL_GQ, tmem_base + D_COL_G + k * 8, make_desc(va + k * 128, DESC_HI), idesc_o, k > 0);
+#pragma unroll
+                for (int k = 0; k < 13; ++k)
+                    umma_bf16_ts(tmem_base + D_COL_GQ, tmem_base + D_COL_G + k * 8, make_desc(dv + k * 128, DESC_HI), idesc_o, 1);
+#pragma unroll
+                for (int k = 0; k < 13; ++k)
+                    umma_bf16_ts(tmem_base + D_COL_GQ, tmem_base + D_COL_A + k * 8, make_desc(dv + k * 128, DESC_HI), idesc_o, 1);
+                umma_commit(o_ready);
+                if (t == 1) umma_commit(empty_v);
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================== softmax / epilogue warps ===========================
+        const int quarter = warp & 3, part = warp >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int cbeg = part == 0 ? 0 : 16 + 48 * part;  // 0, 64, 112, 160
+        for (int u = 0; u < U; ++u) {
+            const int t = u & 1;
+            const int it = blockIdx.x + (u >> 1) * gridDim.x;
+            const int hd = it % H, b = (it / H) % batch, layer = it / (H * batch);
+            mbar_wait(s_ready, u & 1, 86);
+            tc_fence_after();
+            if (part == 0)
+                delta_softmax_part<64>(lane_addr, cbeg, L - cbeg, sMaxA, sMaxW, sSumA, sSumG, sSumB, part, row, quarter);
+            else
+                delta_softmax_part<48>(lane_addr, cbeg, L - cbeg, sMaxA, sMaxW, sSumA, sSumG, sSumB, part, row, quarter);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+            // ---- read the two accumulators out (16 of the 64 output columns per warp) ----
+            mbar_wait(o_ready, u & 1, 87);
+            tc_fence_after();
+            uint32_t na[16], gq[16];
+            tmem_ld_32x32b_x16(lane_addr + D_COL_NA + part * 16, na);
+            tmem_ld_32x32b_x16(lane_addr + D_COL_GQ + part * 16, gq);
+            // o_ready implies every warp arrived on p_ready, i.e. wrote its partial sums before (release / acquire chain)
+            const float la = (sSumA[row] + sSumA[128 + row]) + (sSumA[256 + row] + sSumA[384 + row]);
+            const float dl = (sSumG[row] + sSumG[128 + row]) + (sSumG[256 + row] + sSumG[384 + row]);
+            const float lb = (sSumB[row] + sSumB[128 + row]) + (sSumB[256 + row] + sSumB[384 + row]);
+            tmem_ld_wait();
+            reg_fence(na);
+            reg_fence(gq);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_free);
+            const int q = t * 128 + row;
+            if (q < L) {
+                const float ratio = dl / la, inv = 1.f / fmaxf(lb, 1e-37f);
+                float r[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = fmaf(-ratio, __uint_as_float(na[i]), __uint_as_float(gq[i])) * inv;
+                uint4 w0, w1;
+                w0.x = pack_bf16x2(r[0], r[1]);
+                w0.y = pack_bf16x2(r[2], r[3]);
+                w0.z = pack_bf16x2(r[4], r[5]);
+                w0.w = pack_bf16x2(r[6], r[7]);
+                w1.x = pack_bf16x2(r[8], r[9]);
+                w1.y = pack_bf16x2(r[10], r[11]);
+                w1.z = pack_bf16x2(r[12], r[13]);
+                w1.w = pack_bf16x2(r[14], r[15]);
+                uint4* dst = reinterpret_cast<uint4*>(out + (((int64_t)layer * batch + b) * L + q) * E + hd * HD + part * 16);
+                dst[0] = w0;
+                dst[1] = w1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// =====================================================================================================
 // backward
 // =====================================================================================================
 // delta[b, h, q] = sum_d dO[b, q, h, d] * O[b, q, h, d]   (one warp per token row; 8 lanes per head per 128-bit load)
@@ -1219,6 +1541,29 @@ int launch_attention_pair_tc3(const bf16* qkv_a, const bf16* qkv_b, int64_t ld, 
     const int n_items = layers * batch * H;
     const int grid = n_items < num_sms() ? n_items : num_sms();
     attention_fwd_persistent_kernel<true><<<grid, THREADS, F_SMEM, stream>>>(tmA, tmB, delta, nullptr, L, H, batch, n_items);
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+// delta[layer][batch * L][E] = attention(a + d) - attention(a) in perturbation form; qkv_a: projections of a (with bias),
+// dqkv: projections of the token difference (no bias); both [batch * L, ld] with ld >= layers * 3E
+int launch_attention_delta_tc3(const bf16* qkv_a, const bf16* dqkv, int64_t ld, bf16* delta, int layers, int batch, int L, int H,
+                               cudaStream_t stream) {
+    using namespace attn3;
+    CUtensorMap tmA, tmD;
+    const int64_t E = (int64_t)H * HD;
+    int rc = make_tensor_map_3d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv_a, (uint64_t)layers * 3 * E, L, batch, ld * 2, (uint64_t)L * ld * 2, 64,
+                                BOX_ROWS, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tensor_map_3d(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dqkv, (uint64_t)layers * 3 * E, L, batch, ld * 2, (uint64_t)L * ld * 2, 64,
+                            BOX_ROWS, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    static bool done = false;
+    rc = set_smem(attention_perturb_kernel, D_SMEM, done);
+    if (rc) return rc;
+    const int n_items = layers * batch * H;
+    const int grid = n_items < num_sms() ? n_items : num_sms();
+    attention_perturb_kernel<<<grid, THREADS, D_SMEM, stream>>>(tmA, tmD, delta, L, H, batch, n_items);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }

@@ -221,6 +221,62 @@ colsum_bf16_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ 
     if (c < cols) atomicAdd(out + c, s);
 }
 
+// dst = bf16(scale * src): the perturbation sweep re-uses the unit-noise projections W_qkv (dtok) for every magnitude
+__global__ void __launch_bounds__(EW_THREADS)
+scale_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int64_t n, float scale) {
+    const int64_t n8 = n >> 3;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            o[j] = pack_bf16x2(f.x * scale, f.y * scale);
+        }
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    const int64_t t0 = n8 << 3;
+    for (int64_t i = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = __float2bfloat16_rn(__bfloat162float(src[i]) * scale);
+}
+
+// Counter-based noise for the perturbation sweep: Philox4x32-10 (Salmon et al., SC'11) keyed by the seed, the IMAGE INDEX
+// in the counter, so that the direction drawn for image i depends neither on the batching nor on the sharding over ranks.
+// counter = (j, 0, image_lo, image_hi) -> r0..r3 -> Box-Muller -> elements 4j..4j+3 of the image (oracle/philox_oracle.py).
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ float philox_unit(uint32_t r) { return ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f; }  // 2^-23
+__global__ void __launch_bounds__(EW_THREADS)
+philox_normal_kernel(float* __restrict__ out, int64_t quads_per_image, int64_t total_quads, uint64_t seed, uint64_t first_image) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += stride) {
+        const uint64_t img = first_image + (uint64_t)(q / quads_per_image);
+        const uint32_t j = (uint32_t)(q % quads_per_image);
+        uint32_t c[4] = {j, 0u, (uint32_t)img, (uint32_t)(img >> 32)};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        float4 z;
+        float sn, cs;
+        float rad = sqrtf(-2.f * logf(philox_unit(c[0])));
+        sincospif(2.f * philox_unit(c[1]), &sn, &cs);
+        z.x = rad * cs; z.y = rad * sn;
+        rad = sqrtf(-2.f * logf(philox_unit(c[2])));
+        sincospif(2.f * philox_unit(c[3]), &sn, &cs);
+        z.z = rad * cs; z.w = rad * sn;
+        reinterpret_cast<float4*>(out)[q] = z;
+    }
+}
+
 // out[s] += sum over sample s of (a - b)^2 ; block = (sample, slice)
 __global__ void __launch_bounds__(EW_THREADS)
 rowsumsq_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
@@ -414,6 +470,31 @@ extern "C" int vb_rowsumsq_diff_f32(const float* a, const float* b, float* out, 
     if (slices < 1) slices = 1;
     dim3 grid(n_samples, slices);
     rowsumsq_diff_kernel<<<grid, EW_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(a, b, out, eps);
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+extern "C" int vb_scale_bf16(const void* src, void* dst, int64_t n, float scale, vb_stream_t stream_) {
+    using namespace vb;
+    VB_CHECK_ARG(src && dst && n >= 0, "vb_scale_bf16: bad args");
+    if (n == 0) return VB_OK;
+    VB_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                 "vb_scale_bf16: pointers must be 16B aligned");
+    scale_bf16_kernel<<<ew_grid(n / 8 + 1), EW_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<const bf16*>(src), static_cast<bf16*>(dst), n, scale);
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+extern "C" int vb_philox_normal_f32(float* out, int64_t n_images, int64_t elems_per_image, uint64_t seed, uint64_t first_image,
+                                    vb_stream_t stream_) {
+    using namespace vb;
+    VB_CHECK_ARG(out && n_images >= 0 && elems_per_image > 0, "vb_philox_normal_f32: bad args");
+    VB_CHECK_ARG(elems_per_image % 4 == 0 && elems_per_image / 4 <= 0xFFFFFFFFll, "vb_philox_normal_f32: elems_per_image=%lld must be a multiple of 4 (< 2^34)", (long long)elems_per_image);
+    VB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "vb_philox_normal_f32: out must be 16B aligned");
+    if (n_images == 0) return VB_OK;
+    const int64_t quads = elems_per_image / 4;
+    philox_normal_kernel<<<ew_grid(n_images * quads), EW_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(out, quads, n_images * quads, seed, first_image);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }

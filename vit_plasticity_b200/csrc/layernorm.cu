@@ -399,6 +399,88 @@ layernorm_pair_sqdiff_kernel(const float* __restrict__ a, const float* __restric
     }
 }
 
+// Perturbation form of the kernel above: the second input is given as b = a + scale * d (fp32 token difference d), and the
+// difference of the normalised rows is evaluated without cancellation,
+//   zhat_b - zhat_a = cd * rstd_b + ca * (rstd_b - rstd_a),   ca = a - mean(a),  cd = scale * (d - mean(d)),
+//   rstd_b - rstd_a = -(2 mean(ca cd) + mean(cd^2)) * rstd_a^2 rstd_b^2 / (rstd_a + rstd_b),
+// so a perturbation of relative size 1e-3 (or 1e-6) keeps the full fp32 precision of d; d = 0 gives exactly 0.
+template <int CHUNKS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_delta_sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ d, float scale, float* __restrict__ u,
+                              int n_samples, int rows_per_sample, int cols, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x;
+    const int nchunks = cols >> 2;  // float4 chunks
+    float acc[CHUNKS][4];
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float inv_n = 1.f / (float)cols;
+    for (int r = blockIdx.y * LN_WARPS + warp; r < rows_per_sample; r += gridDim.y * LN_WARPS) {
+        const size_t row = (size_t)s * rows_per_sample + r;
+        const float4* ar = reinterpret_cast<const float4*>(a + row * cols);
+        const float4* dr = reinterpret_cast<const float4*>(d + row * cols);
+        float va[CHUNKS][4], vd[CHUNKS][4];
+        float sa = 0.f, sd = 0.f;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+                const float4 fa = __ldg(ar + c), fd = __ldg(dr + c);
+                va[i][0] = fa.x; va[i][1] = fa.y; va[i][2] = fa.z; va[i][3] = fa.w;
+                vd[i][0] = fd.x * scale; vd[i][1] = fd.y * scale; vd[i][2] = fd.z * scale; vd[i][3] = fd.w * scale;
+                sa += fa.x + fa.y + fa.z + fa.w;
+                sd += (vd[i][0] + vd[i][1]) + (vd[i][2] + vd[i][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { va[i][j] = 0.f; vd[i][j] = 0.f; }
+            }
+        }
+        const float ma = warp_sum(sa) * inv_n, md = warp_sum(sd) * inv_n;
+        float qa = 0.f, qb = 0.f, qx = 0.f, qd = 0.f;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float ca = va[i][j] - ma, cd = vd[i][j] - md, cb = ca + cd;
+                    va[i][j] = ca;
+                    vd[i][j] = cd;
+                    qa += ca * ca;
+                    qb += cb * cb;
+                    qx += ca * cd;
+                    qd += cd * cd;
+                }
+            }
+        }
+        const float var_a = warp_sum(qa) * inv_n, var_b = warp_sum(qb) * inv_n;
+        const float dvar = (2.f * warp_sum(qx) + warp_sum(qd)) * inv_n;  // = var_b - var_a, free of cancellation when small
+        const float ra = rsqrtf(var_a + eps), rb = rsqrtf(var_b + eps);
+        const float dr_ = -dvar * (ra * ra) * (rb * rb) / (ra + rb);      // = rb - ra
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+            const int c = lane + i * 32;
+            if (c < nchunks) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float dz = fmaf(vd[i][j], rb, va[i][j] * dr_);
+                    acc[i][j] += dz * dz;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunks) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(u + (size_t)s * cols + c * 4 + j, acc[i][j]);
+        }
+    }
+}
+
 }  // namespace vb
 
 #define VB_LN_DISPATCH(chunks, CALL)            \
@@ -468,6 +550,20 @@ extern "C" int vb_layernorm_pair_sqdiff(const float* a, const float* b, float* u
     dim3 grid(n_samples, (rows_per_sample + LN_WARPS * 4 - 1) / (LN_WARPS * 4));
     VB_LN_DISPATCH(chunks, (layernorm_pair_sqdiff_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(a, b, u, n_samples,
                                                                                                   rows_per_sample, cols, eps)));
+    VB_CHECK_LAUNCH();
+    return VB_OK;
+}
+
+extern "C" int vb_layernorm_delta_sqdiff(const float* a, const float* d, float scale, float* u, int32_t n_samples,
+                                         int32_t rows_per_sample, int32_t cols, float eps, vb_stream_t stream_) {
+    using namespace vb;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(a && d && u, "vb_layernorm_delta_sqdiff: null pointer");
+    VB_CHECK_ARG(n_samples > 0 && rows_per_sample > 0 && cols % 4 == 0 && cols <= 1024 * 1, "vb_layernorm_delta_sqdiff: cols=%d must be a multiple of 4, <= 1024", cols);
+    const int chunks = (cols / 4 + 31) / 32;
+    dim3 grid(n_samples, (rows_per_sample + LN_WARPS * 4 - 1) / (LN_WARPS * 4));
+    VB_LN_DISPATCH(chunks, (layernorm_delta_sqdiff_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(a, d, scale, u, n_samples,
+                                                                                                   rows_per_sample, cols, eps)));
     VB_CHECK_LAUNCH();
     return VB_OK;
 }

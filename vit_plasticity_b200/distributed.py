@@ -128,6 +128,9 @@ class DataParallel(nn.Module):
         if self.world > 1:
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+                # `.data` has its own version counter: bump the tensor's, or version-keyed caches (the bf16 shadow weights
+                # of ops.shadow_bf16, PlasticityEstimator) built by an earlier forward would keep the pre-broadcast values
+                torch.autograd.graph.increment_version(t)
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)

@@ -113,6 +113,8 @@ class FusedSGD(torch.optim.Optimizer):
         for p in self.trainable:
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                 raise TypeError("FusedSGD needs contiguous fp32 CUDA parameters (there is no CPU path)")
+            if p.data_ptr() % 16 != 0:
+                raise ValueError("FusedSGD: every parameter must be 16-byte aligned (the update kernel uses 128-bit accesses)")
         dev = self.trainable[0].device
         pad4 = lambda n: (n + 3) // 4 * 4
         if grad_arena is not None:  # share DataParallel's flat all-reduce arena
@@ -135,6 +137,9 @@ class FusedSGD(torch.optim.Optimizer):
         self.partials = torch.zeros(1024, device=dev, dtype=torch.float32)  # per-block sums of squares (fixed-order reduction)
         self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self._steps = 0
+        # one shared host scalar plays torch.optim.AdamW's per-parameter state["step"] (torch keeps a CPU fp32 scalar per
+        # parameter by default; every parameter of this optimizer is always at the same step)
+        self._step_tensor = torch.tensor(0.0, dtype=torch.float32)
         self._register_state()
         self.zero_grad()
 
@@ -152,21 +157,37 @@ class FusedSGD(torch.optim.Optimizer):
         for p in self.trainable:
             for key, arena in self._state_arenas().items():
                 self.state[p][key] = self._arena_view(arena, p)
+            if self._has_step_state():
+                self.state[p]["step"] = self._step_tensor
         self.param_groups[0]["fused_steps"] = self._steps
 
+    def _has_step_state(self) -> bool:
+        """torch.optim.SGD keeps no step count in its state; AdamW does (bias correction)."""
+        return False
+
     def load_state_dict(self, state_dict) -> None:
-        """Loaded tensors are copied INTO the arenas (torch would otherwise re-point ``self.state`` at fresh tensors the
-        kernels never read); the step count (first-step momentum initialisation, Adam bias correction) comes back too."""
+        """Accepts state dicts of this class AND of the unfused torch optimizer it replaces (torch.optim.SGD /
+        torch.optim.AdamW: same per-parameter keys). Loaded tensors are copied INTO the arenas (torch would otherwise
+        re-point ``self.state`` at fresh tensors the kernels never read); a parameter without loaded state (torch.optim.SGD
+        before its first step) gets zeros. The step count (Adam bias correction) comes from ``fused_steps`` or, for a torch
+        AdamW checkpoint, from the per-parameter ``state["step"]``."""
         super().load_state_dict(state_dict)
+        steps = self.param_groups[0].get("fused_steps")
         for p in self.trainable:
             st = self.state.get(p, {})
             for key, arena in self._state_arenas().items():
                 view = self._arena_view(arena, p)
                 loaded = st.get(key)
-                if loaded is not None and loaded.data_ptr() != view.data_ptr():
+                if loaded is None:
+                    view.zero_()
+                elif loaded.data_ptr() != view.data_ptr():
                     view.copy_(loaded)
                 self.state[p][key] = view
-        self._steps = int(self.param_groups[0].get("fused_steps", 0))
+            if steps is None and "step" in st:
+                steps = int(float(st["step"]))
+        self._steps = int(steps or 0)
+        self._step_tensor = torch.tensor(float(self._steps), dtype=torch.float32)
+        self._register_state()
 
     def _slot(self, p):
         off = self.offset[p]
@@ -198,6 +219,7 @@ class FusedSGD(torch.optim.Optimizer):
         L.sumsq_partials_f32(self.arena, self.partials)
         self._update(float("inf") if max_norm is None else max_norm)
         self._steps += 1
+        self._step_tensor += 1.0
         self.param_groups[0]["fused_steps"] = self._steps
         for p in self.trainable:  # the kernel wrote through raw pointers: let version-keyed caches (bf16 shadows) see it
             torch.autograd.graph.increment_version(p)
@@ -208,8 +230,10 @@ class FusedSGD(torch.optim.Optimizer):
         from . import _lib as L
 
         group = self.param_groups[0]
+        # first_step = False always: the momentum arena starts at zero, and momentum * 0 + g == g is exactly torch's
+        # first-step "buf = grad"; a special case here would overwrite momentum buffers loaded from a checkpoint
         L.sgd_momentum_clip_step(self.table, self.n_chunks, self.arena, self.momentum_arena, self.partials, self.grad_norm, max_norm,
-                                 group["lr"], group["momentum"], group["weight_decay"], self._steps == 0)
+                                 group["lr"], group["momentum"], group["weight_decay"], False)
 
 
 class FusedAdamW(FusedSGD):
@@ -228,6 +252,9 @@ class FusedAdamW(FusedSGD):
         if not hasattr(self, "exp_avg"):  # (called once from the base constructor, before the moment arenas exist)
             return {}
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+
+    def _has_step_state(self) -> bool:
+        return hasattr(self, "exp_avg")
 
     def _update(self, max_norm: float) -> None:
         from . import _lib as L
@@ -289,7 +316,14 @@ def train_step(model, optimizer, batches, grad_clip: float | None, scheduler=Non
     0-dim device tensors (no host sync here; the reference syncs only every logging period, train.py:297-321)."""
     acc = len(batches)
     loss = None
-    for x, y in batches:
+    # gradient accumulation under data parallelism: only the LAST micro-batch's backward may launch the bucket
+    # all-reduces (DDP.no_sync semantics); earlier micro-batches accumulate locally into the arena. Without this the
+    # overlapped buckets would be reduced during the first backward and later micro-batches would add un-reduced
+    # gradients on top of (and racing with) the collective.
+    syncer = model if hasattr(model, "require_grad_sync") else None
+    for i, (x, y) in enumerate(batches):
+        if syncer is not None:
+            syncer.require_grad_sync = i == acc - 1
         preds = model(x)
         loss = F.cross_entropy(preds, y) / acc
         loss.backward()

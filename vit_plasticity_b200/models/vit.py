@@ -4,7 +4,8 @@ Keeps: the size table (vit.py:130-134), the fixed architecture flags (136-162), 
 ``.model_name`` attributes, ``forward`` / ``get_decomposition`` / ``get_probes`` bound to the inner Transformer as
 instance attributes (173-177), the 2-class head when ``in21k`` (161) and the fresh finetuning head (235-237).
 Loading pretrained weights from a local ``save_dir/<model_name>.pt`` works as in the reference (214-225); the
-HuggingFace download branch (239-303) is out of scope (no network; BASELINE configs are random-init) and raises.
+HuggingFace download branch (239-303) is out of scope (no network; BASELINE configs are random-init): a missing local
+file raises FileNotFoundError instead of silently keeping the random initialisation.
 """
 
 from __future__ import annotations
@@ -60,14 +61,16 @@ class ViT(nn.Module):
             logger.info(f"Initialize new classification head with {self.config.n_classes} classes for finetuning.")
 
     def load_pretrained_weights(self) -> None:
-        """Load ``<save_dir>/<model_name>.pt`` if present; otherwise keep the random initialisation (the reference
-        would download from HuggingFace here, which this offline build does not do)."""
+        """Load ``<save_dir>/<model_name>.pt`` (vit.py:214-225). The reference downloads from HuggingFace when the file is
+        missing (239-303); this offline build cannot, and silently finetuning / analysing a RANDOM model in its place
+        would produce plausible but meaningless numbers, so a missing file raises. Random-init runs (the BASELINE
+        configs) pass ``pretrained=False``."""
         path = Path(self.save_dir) / f"{self.model_name}.pt" if self.save_dir is not None else None
-        if path is not None and os.path.exists(path):
-            logger.info(f"Loading {self.model_name} model from {path}")
-            self.model.load_state_dict(torch.load(path))
-        else:
-            logger.warning(f"No local weights for {self.model_name} under {self.save_dir}; using random initialisation (offline build).")
+        if path is None or not os.path.exists(path):
+            raise FileNotFoundError(f"pretrained=True but there are no local weights for {self.model_name} at {path} (this build does not "
+                                    f"download from HuggingFace); place the converted state_dict there or pass pretrained=False")
+        logger.info(f"Loading {self.model_name} model from {path}")
+        self.model.load_state_dict(torch.load(path))
 
     def set_finetuning_mode(self) -> None:
         head = self.model.output.output_layer

@@ -5,19 +5,21 @@ component output copied to the host), then per key an H2D re-upload and ``distan
 :68), then offline ``ratio = dist[key] / dist["embedding"]`` (apps/plots/analysis.py:97).
 
 Here nothing but the final ``(1 + 5 * n_layers) x N`` table of distances leaves the GPU and no component output or
-difference tensor is ever written to HBM:
+difference tensor is ever written to HBM. A pair is carried as (a, d): the base input a and the DIFFERENCE d = b - a,
+formed in fp32 from the images before anything is rounded to bf16, so the accuracy of every component is independent of
+the size of the perturbation (two independent bf16 evaluations of a and b lose the difference once |d| << |a|: 34-53 %
+error on the attention component at a relative perturbation of 1e-2):
 
 * every block sees the SAME embedding output e (architecture.py:877-881), so the per-layer weights are concatenated
   and each component family is ONE GEMM over all layers;
 * linear components — patch embedding, ``fc1``, ``fc2`` on ``[e,0,0,0]`` (== ``W2[:, :E]``) and the attention output
-  projection — satisfy f(a) - f(b) = W (a - b) (the bias cancels), so the GEMM runs on the difference, computed in
-  fp32 BEFORE the bf16 down-cast, and its epilogue reduces sum(acc^2) per sample straight out of TMEM
-  (``VB_EPI_SUMSQ``);
-* LayerNorm: LN_i(a) - LN_i(b) = gamma_i * (zhat_a - zhat_b), so one fp32 kernel produces
-  u[s, d] = sum_l (zhat_a - zhat_b)^2 and every norm's squared distance is u @ gamma_i^2;
-* attention is non-linear: q/k/v for both inputs come from one concatenated-weight GEMM each, the paired attention
-  kernel subtracts the two head outputs in fp32, and the (linear) output projection runs on that difference with the
-  sum-of-squares epilogue.
+  projection — satisfy f(b) - f(a) = W d (the bias cancels), so the GEMM runs on the difference and its epilogue
+  reduces sum(acc^2) per sample straight out of TMEM (``VB_EPI_SUMSQ``); for a sweep x + eps * n they scale as eps;
+* LayerNorm: LN_i(b) - LN_i(a) = gamma_i * (zhat_b - zhat_a); one fp32 kernel evaluates zhat_b - zhat_a from (a, d)
+  without cancellation (``vb_layernorm_delta_sqdiff``) and every norm's squared distance is u @ gamma_i^2;
+* attention: q/k/v of a and dq/dk/dv = W d come from one concatenated-weight GEMM each; the perturbation-form kernel
+  (``vb_attention_perturb_delta_layers``) forms the score, probability and output differences from those small
+  operands directly, and the (linear) output projection runs on its result with the sum-of-squares epilogue.
 """
 
 from __future__ import annotations
@@ -78,6 +80,91 @@ class PlasticityEstimator:
         self._key = key
 
     # ------------------------------------------------------------------------------------------
+    # the three stages of a pair (a, d): what depends on a only, on d only (linear: scales with |d|), and on both
+    # ------------------------------------------------------------------------------------------
+    def _base(self, x: torch.Tensor) -> dict:
+        """Embedding of the base input (fp32 tokens out of the accumulator + their bf16 copy) and its q/k/v, all layers."""
+        n = x.shape[0]
+        e, nl = self.e, self.n_layers
+        p = L.im2col_patches(x, self.patch)
+        rows_p, kp = p.shape
+        np_ = rows_p // n
+        seq = np_ + 1
+        m = n * seq
+        po = torch.empty(rows_p, e, device=x.device, dtype=torch.float32)
+        L.gemm(p, self.w_patch, m=rows_p, n=e, k=kp, epilogue=L.EPI_F32, bias=self.b_patch, out=po)
+        t16, t32 = L.assemble_tokens(None, po, self.cls, self.pos, n, np_, e, want_bf16=True, want_f32=True)
+        qkv = torch.empty(m, nl * 3 * e, device=x.device, dtype=torch.bfloat16)
+        L.gemm(t16, self.w_qkv, m=m, n=nl * 3 * e, k=e, epilogue=L.EPI_BF16, bias=self.b_qkv, out=qkv)
+        return {"n": n, "np": np_, "seq": seq, "m": m, "t16": t16, "t32": t32, "qkv": qkv}
+
+    def _direction(self, xb: torch.Tensor, xa: torch.Tensor | None) -> dict:
+        """Everything that is linear in the difference d = xb - xa (xa None: xb IS the difference, e.g. a noise
+        direction): embedding distance, fc1 / fc2 distances, the fp32 / bf16 token difference and its q/k/v projections."""
+        n = xb.shape[0]
+        e, f, nl = self.e, self.f, self.n_layers
+        dev = xb.device
+        pd = L.im2col_patches(xb, self.patch, xa)  # (xb - xa) subtracted in fp32, then bf16
+        rows_p, kp = pd.shape
+        np_ = rows_p // n
+        seq = np_ + 1
+        m = n * seq
+        dpo = torch.empty(rows_p, e, device=dev, dtype=torch.float32)
+        L.gemm(pd, self.w_patch, m=rows_p, n=e, k=kp, epilogue=L.EPI_F32, out=dpo)  # the bias cancels in the difference
+        ss_emb = torch.zeros(n, device=dev, dtype=torch.float32)
+        L.rowsumsq_diff_f32(dpo, None, ss_emb, n, np_, e)  # cls / pos rows of the difference are zero
+        d16, d32 = L.assemble_tokens(None, dpo, self.zeros_cls, self.zeros_pos, n, np_, e, want_bf16=True, want_f32=True)
+        ss_fc1 = torch.zeros(n, nl, device=dev, dtype=torch.float32)
+        L.gemm(d16, self.w_fc1, m=m, n=nl * f, k=e, epilogue=L.EPI_SUMSQ, sumsq=ss_fc1, rows_per_sample=seq, cols_per_group=f, n_groups=nl)
+        ss_fc2 = torch.zeros(n, nl, device=dev, dtype=torch.float32)
+        L.gemm(d16, self.w_fc2, m=m, n=nl * e, k=e, epilogue=L.EPI_SUMSQ, sumsq=ss_fc2, rows_per_sample=seq, cols_per_group=e, n_groups=nl)
+        dqkv = torch.empty(m, nl * 3 * e, device=dev, dtype=torch.bfloat16)
+        L.gemm(d16, self.w_qkv, m=m, n=nl * 3 * e, k=e, epilogue=L.EPI_BF16, out=dqkv)
+        return {"ss_emb": ss_emb, "ss_fc1": ss_fc1, "ss_fc2": ss_fc2, "d32": d32, "dqkv": dqkv}
+
+    def _table(self, base: dict, dirn: dict, scale: float, scratch: dict | None = None) -> torch.Tensor:
+        """[1 + 5 n_layers, N] squared distances of the pair (a, a + scale * d)."""
+        n, seq, m = base["n"], base["seq"], base["m"]
+        e, nl, heads = self.e, self.n_layers, self.heads
+        dev = base["t32"].device
+        s2 = float(scale) * float(scale)
+        # ---- LayerNorms: all 2 * n_layers at once ----
+        u = torch.zeros(n, e, device=dev, dtype=torch.float32)
+        L.layernorm_delta_sqdiff(base["t32"], dirn["d32"], scale, u, n, seq, e, self.eps)
+        ss_ln = u @ self.gamma_sq  # [N, 2 * n_layers]; 2*N*E*2n_layers FLOPs, negligible
+        # ---- attention (applied to the un-normalised embedding, architecture.py:405) ----
+        ss_attn = torch.zeros(n, nl, device=dev, dtype=torch.float32)
+        scratch = scratch if scratch is not None else {}
+        if scale == 1.0:
+            dqkv = dirn["dqkv"]
+        else:
+            buf = scratch.get("dqkv")
+            if buf is None or buf.shape != dirn["dqkv"].shape:
+                buf = scratch["dqkv"] = torch.empty_like(dirn["dqkv"])
+            dqkv = L.scale_bf16(dirn["dqkv"], scale, buf)
+        if seq <= 208:
+            out = scratch.get("delta")
+            if out is None or out.shape != (nl, m, e):
+                out = scratch["delta"] = torch.empty(nl, m, e, device=dev, dtype=torch.bfloat16)
+            delta_all = L.attention_perturb_delta_layers(base["qkv"], dqkv, nl, n, seq, heads, e // heads, out=out)  # one launch, all layers
+        else:
+            # longer sequences (ViT-H/14: 257 tokens) have no perturbation-form kernel: two independent evaluations on the
+            # mma.sync path, accurate for perturbations of the order of the input only
+            qkv_b = L.add_bf16(base["qkv"], dqkv)
+            delta_all = torch.empty(nl, m, e, device=dev, dtype=torch.bfloat16)
+            for i in range(nl):
+                qa, qb = base["qkv"][:, i * 3 * e : (i + 1) * 3 * e], qkv_b[:, i * 3 * e : (i + 1) * 3 * e]
+                L.attention_pair_delta(qb, qa, delta_all[i], n, seq, heads, e // heads)
+        for i in range(nl):
+            # sumsq pointer offset by i with n_groups = n_layers writes column i of ss_attn
+            L.gemm(delta_all[i], self.w_out[i], m=m, n=e, k=e, epilogue=L.EPI_SUMSQ, sumsq=ss_attn[:, i:], rows_per_sample=seq, cols_per_group=e, n_groups=nl)
+        # ---- assemble in the reference's key order; the linear components scale with the perturbation ----
+        rows = [dirn["ss_emb"] * s2]
+        for i in range(nl):
+            rows += [ss_ln[:, i], ss_attn[:, i], ss_ln[:, nl + i], dirn["ss_fc1"][:, i] * s2, dirn["ss_fc2"][:, i] * s2]
+        return torch.stack(rows, 0)
+
+    # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def squared_distances(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
         """f32 device tensor [1 + 5 * n_layers, N] of SQUARED distances, rows ordered like the reference's keys."""
@@ -85,58 +172,19 @@ class PlasticityEstimator:
             raise RuntimeError("PlasticityEstimator runs on CUDA only — there is no CPU fallback")
         self._refresh()
         x1, x2 = x1.float().contiguous(), x2.float().contiguous()
-        n = x1.shape[0]
-        e, f, nl, heads = self.e, self.f, self.n_layers, self.heads
-        dev = x1.device
-        # ---- embedding of both inputs (fp32 out of the accumulator) and of the difference ----
-        p1, p2 = L.im2col_patches(x1, self.patch), L.im2col_patches(x2, self.patch)
-        pd = L.im2col_patches(x1, self.patch, x2)  # (x1 - x2) subtracted in fp32, then bf16
-        rows_p, kp = p1.shape
-        np_ = rows_p // n
-        seq = np_ + 1
-        m = n * seq
-        emb = []
-        for p in (p1, p2):
-            po = torch.empty(rows_p, e, device=dev, dtype=torch.float32)
-            L.gemm(p, self.w_patch, m=rows_p, n=e, k=kp, epilogue=L.EPI_F32, bias=self.b_patch, out=po)
-            emb.append(L.assemble_tokens(None, po, self.cls, self.pos, n, np_, e, want_bf16=True, want_f32=True))
-        (t1_16, t1_32), (t2_16, t2_32) = emb
-        ss_emb = torch.zeros(n, 1, device=dev, dtype=torch.float32)
-        L.gemm(pd, self.w_patch, m=rows_p, n=e, k=kp, epilogue=L.EPI_SUMSQ, sumsq=ss_emb, rows_per_sample=np_, cols_per_group=e, n_groups=1)
-        dpo = torch.empty(rows_p, e, device=dev, dtype=torch.bfloat16)
-        L.gemm(pd, self.w_patch, m=rows_p, n=e, k=kp, epilogue=L.EPI_BF16, out=dpo)
-        dtok, _ = L.assemble_tokens(dpo, None, self.zeros_cls, self.zeros_pos, n, np_, e)  # cls row of the difference is 0
-        # ---- LayerNorms: all 2 * n_layers at once ----
-        u = torch.zeros(n, e, device=dev, dtype=torch.float32)
-        L.layernorm_pair_sqdiff(t1_32, t2_32, u, n, seq, e, self.eps)
-        ss_ln = u @ self.gamma_sq  # [N, 2 * n_layers]; 2*N*E*2n_layers FLOPs, negligible
-        # ---- fc1 / fc2 on the difference, all layers in one GEMM each ----
-        ss_fc1 = torch.zeros(n, nl, device=dev, dtype=torch.float32)
-        L.gemm(dtok, self.w_fc1, m=m, n=nl * f, k=e, epilogue=L.EPI_SUMSQ, sumsq=ss_fc1, rows_per_sample=seq, cols_per_group=f, n_groups=nl)
-        ss_fc2 = torch.zeros(n, nl, device=dev, dtype=torch.float32)
-        L.gemm(dtok, self.w_fc2, m=m, n=nl * e, k=e, epilogue=L.EPI_SUMSQ, sumsq=ss_fc2, rows_per_sample=seq, cols_per_group=e, n_groups=nl)
-        # ---- attention (applied to the un-normalised embedding, architecture.py:405) ----
-        ss_attn = torch.zeros(n, nl, device=dev, dtype=torch.float32)
-        qkv = []
-        for t in (t1_16, t2_16):
-            q = torch.empty(m, nl * 3 * e, device=dev, dtype=torch.bfloat16)
-            L.gemm(t, self.w_qkv, m=m, n=nl * 3 * e, k=e, epilogue=L.EPI_BF16, bias=self.b_qkv, out=q)
-            qkv.append(q)
-        if seq <= 208:
-            delta_all = L.attention_pair_delta_layers(qkv[0], qkv[1], nl, n, seq, heads, e // heads)  # one launch, all layers
-        else:
-            delta_all = torch.empty(nl, m, e, device=dev, dtype=torch.bfloat16)
-            for i in range(nl):
-                qa, qb = qkv[0][:, i * 3 * e : (i + 1) * 3 * e], qkv[1][:, i * 3 * e : (i + 1) * 3 * e]
-                L.attention_pair_delta(qa, qb, delta_all[i], n, seq, heads, e // heads)
-        for i in range(nl):
-            # sumsq pointer offset by i with n_groups = n_layers writes column i of ss_attn
-            L.gemm(delta_all[i], self.w_out[i], m=m, n=e, k=e, epilogue=L.EPI_SUMSQ, sumsq=ss_attn[:, i:], rows_per_sample=seq, cols_per_group=e, n_groups=nl)
-        # ---- assemble in the reference's key order ----
-        rows = [ss_emb[:, 0]]
-        for i in range(nl):
-            rows += [ss_ln[:, i], ss_attn[:, i], ss_ln[:, nl + i], ss_fc1[:, i], ss_fc2[:, i]]
-        return torch.stack(rows, 0)
+        return self._table(self._base(x1), self._direction(x2, x1), 1.0)
+
+    @torch.no_grad()
+    def sweep_squared_distances(self, x: torch.Tensor, direction: torch.Tensor, eps_list) -> list[torch.Tensor]:
+        """Tables of the pairs (x, x + eps * direction) for every eps: f(x) and everything linear in the direction are
+        computed once and shared by the whole grid (apps/plots/loss_landscape.py:180-191 style magnitude sweep)."""
+        if not (x.is_cuda and direction.is_cuda):
+            raise RuntimeError("PlasticityEstimator runs on CUDA only — there is no CPU fallback")
+        self._refresh()
+        base = self._base(x.float().contiguous())
+        dirn = self._direction(direction.float().contiguous(), None)
+        scratch: dict = {}
+        return [self._table(base, dirn, float(eps), scratch) for eps in eps_list]
 
     def keys(self) -> list[str]:
         if self._key is None:
@@ -156,58 +204,82 @@ class PlasticityEstimator:
         return {k: table[j] for j, k in enumerate(self.keys())}
 
 
-def gather_tables(local: np.ndarray, n_total: int, group=None) -> np.ndarray | None:
-    """Concatenate the ranks' [rows, n_local] distance tables along the pair axis on rank 0 (contiguous shards in rank
-    order, see ``distributed.shard_range``). The only collective of the sweep: one gather at the end."""
+def gather_tables(local: torch.Tensor, n_total: int, per_rank: int, group=None) -> torch.Tensor | None:
+    """Concatenate the ranks' [..., n_local] distance tables along the pair axis on rank 0 (contiguous shards in rank
+    order, see ``distributed.shard_range``; every rank pads to ``per_rank`` columns). The only collective of the sweep:
+    ONE gather at the end (NCCL on GPUs; the gloo CPU tests gather host tensors)."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    parts = [None] * world if rank == 0 else None
-    dist.gather_object(local, parts, dst=0, group=group)
+    if dist.get_backend(group) != "nccl":
+        local = local.cpu()
+    padded = local.new_zeros(*local.shape[:-1], per_rank)
+    padded[..., : local.shape[-1]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded.contiguous(), parts, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     if rank != 0:
         return None
-    table = np.concatenate(parts, axis=1)
-    assert table.shape[1] == n_total, (table.shape, n_total)
+    # shards are contiguous; only the tail ranks are short (or empty): drop every rank's padding
+    table = torch.cat([parts[r][..., : max(0, min(per_rank, n_total - r * per_rank))] for r in range(world)], -1)
+    assert table.shape[-1] == n_total, (table.shape, n_total)
     return table
 
 
+def sweep_noise(n_images: int, image_shape, noise_seed: int, first_image: int, device) -> torch.Tensor:
+    """Perturbation directions of images [first_image, first_image + n_images): standard normals drawn ON THE DEVICE from
+    Philox4x32-10 keyed by ``noise_seed`` with the image index in the counter (``vb_philox_normal_f32``), so the noise of
+    an image depends neither on the batching nor on the sharding over ranks."""
+    return L.philox_normal(n_images, tuple(image_shape), noise_seed, first_image, device)
+
+
 def perturbation_sweep(model, images, eps_list, noise_seed: int = 0, pairs_per_call: int = 64, rank: int | None = None,
-                       world: int | None = None, group=None, estimator: "PlasticityEstimator | None" = None):
+                       world: int | None = None, group=None, estimator: "PlasticityEstimator | None" = None, stats: dict | None = None):
     """Plasticity under input perturbations of growing magnitude (BASELINE.json configs[4]): pairs (x, x + eps * n),
-    n ~ N(0, 1) drawn per image from ``noise_seed``, for every eps in ``eps_list``.
+    n ~ N(0, 1) per image from ``noise_seed`` (:func:`sweep_noise`), for every eps in ``eps_list``.
 
     The N images are sharded contiguously over the ranks (each pair is independent: apps/vit/analysis.py:68 reduces per
-    sample); every rank streams its shard from ``images`` (host or device, fp32 NCHW) through the fused estimator and
-    only the (1 + 5 n_layers) x N_local distance table per eps leaves the GPU. No collective on the data path; rank 0
-    receives {eps: {key: (N,) float32}} from one gather per eps at the end, the other ranks get None.
+    sample); every rank streams its shard from ``images`` (host or device, fp32 NCHW) through the fused estimator:
+    x + eps * n is never formed — the pair is carried as (x, eps * n), f(x) and everything linear in n are shared by the
+    whole eps grid — and only the (1 + 5 n_layers) x N_local distance table per eps leaves the GPU. No collective on
+    the data path; rank 0 receives {eps: {key: (N,) float32}} from ONE gather at the end, the other ranks get None.
+    ``stats`` (optional dict) receives ``gather_s``, the wall time of that gather.
     """
+    import time
+
+    import torch.distributed as dist
+
     from .distributed import shard_range
 
     est = estimator if estimator is not None else PlasticityEstimator(model)
     n_total = images.shape[0]
     lo, hi = shard_range(n_total, rank, world)
     dev = next(_inner(model).parameters()).device
-    tables = {float(e): [] for e in eps_list}
+    eps_list = [float(e) for e in eps_list]
+    keys = est.keys()
+    chunks: list[torch.Tensor] = []
     for s0 in range(lo, hi, pairs_per_call):
         s1 = min(s0 + pairs_per_call, hi)
         x = images[s0:s1].to(dev, non_blocking=True).float()
-        # per-image generators: the noise of image i does not depend on how the images are sharded or batched
-        noise = torch.stack([torch.randn(x.shape[1:], generator=torch.Generator().manual_seed(noise_seed * 1_000_003 + i)) for i in range(s0, s1)]).to(dev)
-        for e in eps_list:
-            tables[float(e)].append(est.squared_distances(x, x + float(e) * noise).sqrt())
-    out = {}
-    keys = est.keys()
-    for e, chunks in tables.items():
-        local = torch.cat(chunks, 1).cpu().numpy() if chunks else np.zeros((len(keys), 0), np.float32)
-        table = gather_tables(local, n_total, group)
-        out[e] = None if table is None else {k: table[j] for j, k in enumerate(keys)}
-    import torch.distributed as dist
-
-    if dist.is_available() and dist.is_initialized() and dist.get_rank(group) != 0:
+        noise = sweep_noise(s1 - s0, x.shape[1:], noise_seed, s0, dev)
+        chunks.append(torch.stack(est.sweep_squared_distances(x, noise, eps_list), 0).sqrt())  # [n_eps, rows, n_chunk]
+    local = torch.cat(chunks, 2) if chunks else torch.zeros(len(eps_list), len(keys), 0, device=dev)
+    distributed = dist.is_available() and dist.is_initialized() and (world is None or world == dist.get_world_size(group))
+    t0 = time.perf_counter()
+    if distributed and dist.get_world_size(group) > 1:
+        w = dist.get_world_size(group)
+        table = gather_tables(local, n_total, (n_total + w - 1) // w, group)
+        if local.is_cuda:
+            torch.cuda.synchronize()
+    else:
+        table = local
+    if stats is not None:
+        stats["gather_s"] = time.perf_counter() - t0
+    if table is None:
         return None
-    return out
+    table = table.cpu().numpy()
+    return {e: {k: table[i, j] for j, k in enumerate(keys)} for i, e in enumerate(eps_list)}
 
 
 def analysis(model, loader1, loader2, n_steps: int, save_dir=None, device=None) -> dict[str, np.ndarray]:
