@@ -1,16 +1,20 @@
-"""Headline benchmark: ViT-B/16 bf16 finetuning images/s on B200 (BASELINE.json configs[1]), plus the plasticity
-estimator's pairs/s (configs[0] shapes) as a secondary block of the same JSON line.
+"""Headline benchmark: ViT-B/16 bf16 finetuning images/s on B200 (BASELINE.json configs[1]); the plasticity estimator's
+pairs/s (configs[0] shapes) and a bounded ViT-L/16 perturbation sweep (configs[4] shapes) ride along as secondary blocks
+of the same JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--model base|large] [--components ...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model base|large] [--components ...] [--scaling strong|weak]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference     # the reference algorithm's CPU path (oracle port) on the host cores
+    python bench.py --workload sweep [--images 65536] [--eps 1e-3,1e-2,1e-1,1,10]   # configs[4] in full (ViT-L/16)
+    python bench.py --impl reference     # the UNMODIFIED reference (baseline/_ref) on the host cores
 
-A step = forward + cross-entropy + backward + grad-norm clip + SGD-momentum step on one synthetic batch
-(apps/vit/train.py:263-283 semantics). ``value`` times K steps with the batch already resident in HBM; ``e2e`` times
-the same K steps through the public API with the batch in pinned HOST memory (H2D copy of the images and labels and a
-D2H read of the loss inside the timed region, every step). Timing: CUDA events around the K steps, barrier +
-synchronize on both sides, max over ranks. L2 (126 MB) cannot carry anything between steps: one step streams
-> 30 GB of activations (config.l2 = "inputs>L2").
+Finetuning: a step = forward + cross-entropy + backward + grad-norm clip + SGD-momentum step on one synthetic batch
+(apps/vit/train.py:263-283 semantics). N = 1 runs batch 512 (configs[1]). N > 1 runs the split BASELINE.json configs[2]/[3]
+and SURVEY.md 8(e) state: GLOBAL batch 512, 512 / N images per rank ("scaling": "strong"); `--scaling weak` keeps
+`--batch` images per rank instead. ``value`` times K steps with the batch already resident in HBM; ``e2e`` times the
+same K steps through the public API with the batch in pinned HOST memory (H2D copy of the images and labels and a D2H
+read of the loss inside the timed region, every step). Timing: CUDA events around the K steps, barrier + synchronize on
+both sides, max over ranks. L2 (126 MB) cannot carry anything between steps: one step streams > 30 GB of activations at
+batch 512, > 3.8 GB at batch 64 (config.l2 = "inputs>L2").
 """
 
 from __future__ import annotations
@@ -28,7 +32,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FWD_GFLOP_PER_IMG = {"base": 35.126, "large": 123.107}  # SURVEY.md Appendix D (2 FLOPs per MAC)
-PLAST_GFLOP_PER_PAIR = {"base": 39.577, "large": 137.146}  # executed variant: fc1/fc2/patch/proj on the difference
+VIT = {"base": dict(e=768, h=12, nl=12, f=3072), "large": dict(e=1024, h=16, nl=24, f=4096)}
+SEQ, NP, KP = 197, 196, 3 * 16 * 16
+EPS_GRID = "1e-3,1e-2,1e-1,1,10"
 
 
 def parse():
@@ -36,24 +42,49 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (weak scaling)")
-    ap.add_argument("--model", default="base")
+    ap.add_argument("--workload", default="finetune", choices=["finetune", "sweep"])
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"], help="N > 1: strong = global batch split over the ranks (default), weak = --batch per rank")
+    ap.add_argument("--global-batch", type=int, default=512, help="global batch of the strong-scaling split (BASELINE.json configs[2]/[3])")
+    ap.add_argument("--batch", type=int, default=512, help="per-GPU batch at N = 1 and under --scaling weak")
+    ap.add_argument("--model", default=None, help="base | large (default: base for finetune, large for sweep)")
     ap.add_argument("--components", default="", help="comma-separated components to FREEZE (apps/vit/utils.py:67-74)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=64, help="plasticity pairs per call (0 disables the secondary block)")
+    ap.add_argument("--images", type=int, default=65536, help="--workload sweep: images in total (sharded over the ranks)")
+    ap.add_argument("--eps", default=EPS_GRID, help="perturbation magnitudes of the sweep")
+    ap.add_argument("--sweep-images", type=int, default=256, help="images per rank of the secondary ViT-L sweep block (0 disables it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the informational block: reference modules eager on the same GPU")
     ap.add_argument("--torch-sgd", action="store_true", help="clip_grad_norm_ + torch.optim.SGD instead of the fused arena step")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.model is None:
+        args.model = "large" if args.workload == "sweep" else "base"
+    if args.scaling is None:
+        args.scaling = "strong"
+    return args
 
 
-def workload_config(model_name: str, batch: int, world: int, comps, n_trainable=None):
-    """The `config` object shared by both arms (the reference arm runs a bounded sample of the same workload)."""
-    cfg = {"workload": f"ViT-{model_name}/16 finetuning (fwd + CE + bwd + clip 1.0 + SGD 1e-2 m0.9), batch {batch}/GPU, 10-class synthetic CIFAR-10-shaped 224x224, random init",
-           "global_batch": batch * world, "parallelism": f"dp{world}", "freeze": comps}
-    if n_trainable is not None:
-        cfg["trainable_params"] = n_trainable
-    return cfg
+def per_rank_batch(args, world: int) -> int:
+    if world == 1 or args.scaling == "weak":
+        return args.batch
+    if args.global_batch % world:
+        raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+    return args.global_batch // world
+
+
+def finetune_config(model_name: str, batch: int, world: int, comps, n_trainable, scaling: str):
+    """The `config` object of the finetuning line, identical for both arms (the reference arm times a bounded sample of it)."""
+    return {"workload": f"ViT-{model_name}/16 finetuning (fwd + CE + bwd + clip 1.0 + SGD 1e-2 m0.9), batch {batch}/GPU, 10-class synthetic CIFAR-10-shaped 224x224, random init",
+            "global_batch": batch * world, "parallelism": f"dp{world}", "freeze": comps, "trainable_params": n_trainable,
+            "scaling": scaling if world > 1 else "single GPU", "l2": "inputs>L2 (one step streams GBs of activations)"}
+
+
+def sweep_config(model_name: str, images: int, eps, world: int, pairs_per_call: int):
+    return {"workload": f"ViT-{model_name}/16 plasticity sweep: {images} images x {len(eps)} perturbation magnitudes {eps} = {images * len(eps)} pairs (x, x + eps n), "
+                        f"n ~ N(0,1) drawn on the device, 224x224 synthetic CIFAR-10-shaped inputs, random init",
+            "images": images, "eps": eps, "parallelism": f"pairs sharded contiguously over {world} rank(s), no data-path collective, one gather at the end",
+            "pairs_per_call": pairs_per_call, "l2": "inputs>L2 (one call streams > 4 GB of projections)"}
 
 
 def ncu_traffic_per_launch():
@@ -86,6 +117,24 @@ def peaks():
         except Exception:
             pass
     return p
+
+
+def sweep_gflop(model_name: str, n_eps: int) -> dict:
+    """FLOPs the fused estimator EXECUTES per image of a sweep over n_eps magnitudes (2 per MAC), and what the reference's
+    procedure (two full get_decomposition passes per pair, fc2 on the zero-padded 4E input) would spend on the same pairs."""
+    v = VIT[model_name]
+    e, h, nl, f = v["e"], v["h"], v["nl"], v["f"]
+    patch = 2.0 * NP * e * KP
+    qkv = 2.0 * SEQ * e * 3 * e * nl
+    fc1 = 2.0 * SEQ * e * f * nl
+    fc2 = 2.0 * SEQ * e * e * nl
+    proj = 2.0 * SEQ * e * e * nl
+    core = 2.0 * SEQ * SEQ * 64 * h * nl  # one score-shaped or P V-shaped contraction over all heads and layers
+    shared = 2 * patch + 2 * qkv + fc1 + fc2          # base + direction embeddings and projections, fc1 / fc2 on the direction
+    per_eps = 8 * core + proj                          # S, 3 x dS, 4 x P V; output projection of the difference
+    faithful_pair = 2 * (patch + qkv + 2 * core + proj + fc1 + 2.0 * SEQ * f * e * nl)  # reference-faithful count per pair
+    return {"executed_per_image": (shared + n_eps * per_eps) / 1e9, "executed_per_pair": (shared / n_eps + per_eps) / 1e9,
+            "reference_faithful_per_pair": faithful_pair / 1e9}
 
 
 class ClockSampler:
@@ -132,29 +181,36 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# reference arm / cpu baseline: the UNMODIFIED reference (baseline/_ref) on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_finetune_img_s(model_name: str, batch: int, steps: int, warmup: int, components):
+CPU_SAMPLE_BATCH = 8  # images per step of the CPU arm: a bounded sample of the batch-512 workload (CPU minutes otherwise)
+
+
+def cpu_reference_baseline(model_name: str, comps, steps: int, warmup: int, with_omp1: bool, plasticity_pairs: int):
+    """cpu_baseline object: the reference's own step on all host cores (`value`), the reference-faithful OMP_NUM_THREADS=1
+    setting the apps force at import (train.py:16, analysis.py:14) beside it, and configs[0] in full for the estimator."""
     import torch
 
-    from oracle import vit_oracle as O
+    from baseline import reference_arm as R
 
+    why = R.available()
+    if why is not None:  # never silently substitute the port: say what is missing
+        return {"unavailable": why}, None
     cores = os.cpu_count() or 1
+    v, dt, n_trainable = R.finetune(model_name, CPU_SAMPLE_BATCH, steps, warmup, comps, cores)
+    out = {"value": round(v, 3), "unit": "img/s", "cores": cores, "kind": "reference",
+           "sample": f"unmodified reference (baseline/_ref: vitef.models.build_model ViT-{model_name}/16 -> F.cross_entropy -> backward -> clip_grad_norm_ -> "
+                     f"vitef.optim SGD) fp32 on {cores} host threads, batch {CPU_SAMPLE_BATCH} per step (of the batch-512 workload), median of {steps} steps after {warmup} warm-up, {dt:.2f} s/step"}
+    if with_omp1:
+        v1, dt1, _ = R.finetune(model_name, CPU_SAMPLE_BATCH, max(2, min(steps, 3)), 1, comps, 1)
+        out["omp_num_threads_1"] = {"value": round(v1, 3), "unit": "img/s", "cores": 1, "s_per_step": round(dt1, 2),
+                                    "note": "reference-faithful threading: the apps set OMP_NUM_THREADS=1 at import (apps/vit/train.py:16)"}
+    if plasticity_pairs > 0:
+        pv, pdt = R.plasticity("base", plasticity_pairs, 16, cores)
+        out["plasticity"] = {"value": round(pv, 3), "unit": "pairs/s", "cores": cores, "kind": "reference", "pairs": plasticity_pairs, "seconds": round(pdt, 2),
+                             "sample": f"BASELINE.json configs[0] in full: ViT-B/16, {plasticity_pairs} synthetic pairs, get_decomposition x 2 + apps.vit.analysis.distance per key, fp32 CPU, {cores} threads"}
     torch.set_num_threads(cores)
-    arch = O.vit_arch(model_name, n_classes=10)
-    sd = O.init_state_dict(arch, seed=42)
-    frozen = O.frozen_keys(sd, components)
-    x, y = O.synthetic_images(batch, arch, 1), O.synthetic_labels(batch, arch, 2)
-    bufs = {}
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        _, _, grads = O.loss_and_grads(sd, x, y, arch, frozen)
-        O.sgd_step(sd, bufs, grads, 1e-2, 0.9, 1.0)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    dt = sum(times) / len(times)
-    return batch / dt, dt, cores
+    return out, n_trainable
 
 
 def run_reference(args):
@@ -162,48 +218,166 @@ def run_reference(args):
     if rank != 0:
         return
     comps = [c for c in args.components.split(",") if c]
-    batch = 8  # bounded sample of the batch-512 workload: same step, 8 images per step (CPU minutes otherwise)
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    v, dt, cores = cpu_finetune_img_s(args.model, batch, steps, warmup, comps)
-    sample = f"oracle port (torch fp32 CPU) of apps/vit/train.py step, ViT-{args.model}/16, batch {batch} (of the 512 workload), {steps} timed steps"
+    world = max(1, args.gpus)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    if args.workload == "sweep":
+        eps = [float(e) for e in args.eps.split(",")]
+        return run_reference_sweep(args, eps, world)
+    cpu, n_trainable = cpu_reference_baseline(args.model, comps, steps, warmup, with_omp1=False, plasticity_pairs=0)
+    if "unavailable" in cpu:
+        print(json.dumps({"impl": "reference", "unavailable": cpu["unavailable"]}))
+        return
+    v = cpu["value"]
     print(json.dumps({
-        "impl": "reference", "metric": f"ViT-{args.model[0].upper()}/16 finetune img/s", "value": round(v, 3), "unit": "img/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args.model, args.batch, max(1, args.gpus), comps), sample="CPU arm: bounded sample of the workload, 8 images per step"),
-        "cpu_baseline": {"value": round(v, 3), "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": round(v, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": f"ViT-{args.model[0].upper()}/16 finetune img/s", "value": v, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(CPU_SAMPLE_BATCH / v * 1e3, 2), "higher_is_better": True,
+        "scaling": "strong" if (world > 1 and args.scaling == "strong") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": finetune_config(args.model, per_rank_batch(args, world), world, comps, n_trainable, args.scaling),
+        "cpu_baseline": cpu,
+        "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def run_reference_sweep(args, eps, world):
+    """Reference procedure for the sweep on the host cores: per image and magnitude, get_decomposition(x) and
+    get_decomposition(x + eps n) + distance per key (f(x) recomputed per pair, exactly as apps/vit/analysis.py would)."""
+    import torch
+
+    from baseline import reference_arm as R
+
+    why = R.available()
+    if why is not None:
+        print(json.dumps({"impl": "reference", "unavailable": why}))
+        return
+    cores = os.cpu_count() or 1
+    pairs = max(2, min(8, args.steps))  # bounded sample: a handful of ViT-L pairs (~4 s each on 16 threads)
+    v, dt = R.plasticity(args.model, pairs, 2, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": f"ViT-{args.model[0].upper()}/16 plasticity sweep pairs/s", "value": round(v, 4), "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": sweep_config(args.model, args.images, eps, world, 64),
+        "cpu_baseline": {"value": round(v, 4), "unit": "pairs/s", "cores": cores, "kind": "reference",
+                         "sample": f"unmodified reference estimator (ViT.get_decomposition x 2 + apps.vit.analysis.distance) on {pairs} ViT-{args.model}/16 pairs, fp32, {cores} threads, {dt:.1f} s"},
+        "e2e": {"value": round(v, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    torch.set_num_threads(cores)
 
 
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+class Ctx:
+    """Process-wide state of the B200 arm: device, ranks, timing helper."""
 
-    import torch
-    import torch.distributed as dist
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    from vit_plasticity_b200 import _lib, build_model
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs CUDA devices: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device(f"cuda:{self.local}")
+        if self.world > 1:
+            dist.init_process_group(backend="nccl", device_id=self.dev)
+        self.pk = peaks()
+
+    def timed(self, fn_step, steps):
+        """CUDA events around `steps` calls, barrier + synchronize on both sides, MAX over ranks (ms)."""
+        torch, dist = self.torch, self.dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn_step(i)
+        e.record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def build_vit(ctx, model_name: str):
+    from vit_plasticity_b200 import build_model
+
+    ctx.torch.manual_seed(42)
+    return build_model({"implementation": "vit", "model_name": model_name, "pretrained": False, "in21k": True, "finetuning": True, "n_classes": 10}, device=ctx.dev)
+
+
+def dp_parity_check(ctx, model, dp, opt, global_batch: int):
+    """One optimisation step on IDENTICAL data two ways, from identical weights: (a) through DataParallel, every rank on its
+    contiguous shard of the batch, gradients averaged by the bucketed all-reduce; (b) every rank alone on the whole batch
+    (no collective). Compares the pre-clip gradient norm and a checksum of the updated parameters between (a) and (b) and
+    across ranks. Weights and optimizer state are restored afterwards."""
+    torch, dist = ctx.torch, ctx.dist
+    from vit_plasticity_b200.finetune import train_step
+
+    n = min(global_batch, 512)
+    n -= n % ctx.world
+    g = torch.Generator().manual_seed(99)
+    x, y = torch.randn(n, 3, 224, 224, generator=g).to(ctx.dev), torch.randint(0, 10, (n,), generator=g).to(ctx.dev)
+    params = [p for p in model.parameters()]
+    saved = [p.detach().clone() for p in params]
+
+    def restore():
+        with torch.no_grad():
+            for p, s in zip(params, saved):
+                p.copy_(s)
+        if getattr(opt, "momentum_arena", None) is not None:
+            opt.momentum_arena.zero_()
+        opt._steps = 0
+        opt.zero_grad()
+
+    def checksum():
+        return torch.stack([p.detach().double().sum() for p in params if p.requires_grad]).sum(), torch.stack([p.detach().double().abs().sum() for p in params if p.requires_grad]).sum()
+
+    per = n // ctx.world
+    lo = ctx.rank * per
+    _, gn_dp = train_step(dp, opt, [(x[lo : lo + per], y[lo : lo + per])], grad_clip=1.0, after_backward=dp.finish_grad_sync)
+    cs_dp = checksum()
+    gn_dp = gn_dp.double().clone()
+    delta_dp = torch.sqrt(sum(((p.detach() - s).double() ** 2).sum() for p, s in zip(params, saved) if p.requires_grad))
+    restore()
+    dp.require_grad_sync = False  # (b): local gradients only, no bucket is launched
+    _, gn_one = train_step(model, opt, [(x, y)], grad_clip=1.0)
+    dp.require_grad_sync = True
+    cs_one = checksum()
+    upd_diff = torch.sqrt(sum(((p.detach() - s).double() ** 2).sum() for p, s in zip(params, saved) if p.requires_grad))
+    gn_one = gn_one.double().clone()
+    restore()
+    mine = torch.stack([gn_dp, cs_dp[0], cs_dp[1]]).to(ctx.dev)
+    allr = [torch.empty_like(mine) for _ in range(ctx.world)]
+    dist.all_gather(allr, mine)
+    allr = torch.stack(allr)
+    replicas_identical = bool((allr == allr[0]).all())
+    rel = lambda a, b: abs(float(a) - float(b)) / max(abs(float(b)), 1e-30)
+    out = {"global_batch": n, "ranks": ctx.world, "grad_norm_dp": float(gn_dp), "grad_norm_single_process": float(gn_one),
+           "grad_norm_rel_diff": rel(gn_dp, gn_one), "param_abs_checksum_rel_diff": rel(cs_dp[1], cs_one[1]),
+           "update_norm_rel_diff": rel(delta_dp, upd_diff), "replicas_bit_identical": replicas_identical}
+    out["pass"] = bool(replicas_identical and out["grad_norm_rel_diff"] <= 1e-3 and out["update_norm_rel_diff"] <= 1e-3)
+    return out
+
+
+def bench_finetune(ctx, args):
+    torch, dist = ctx.torch, ctx.dist
+    from vit_plasticity_b200 import _lib
     from vit_plasticity_b200.distributed import DataParallel
     from vit_plasticity_b200.finetune import build_optimizer, freeze_model, train_step
     from vit_plasticity_b200.plasticity import PlasticityEstimator
 
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs CUDA devices: the product path has no CPU fallback (use --impl reference for the CPU arm)")
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    if world > 1:
-        dist.init_process_group(backend="nccl", device_id=dev)
+    rank, world, dev, pk = ctx.rank, ctx.world, ctx.dev, ctx.pk
     comps = [c for c in args.components.split(",") if c]
-    pk = peaks()
-
-    torch.manual_seed(42)
-    model = build_model({"implementation": "vit", "model_name": args.model, "pretrained": False, "in21k": True, "finetuning": True, "n_classes": 10}, device=dev)
+    model = build_vit(ctx, args.model)
     model.train()
     freeze_model(model, comps)
     n_trainable = sum(p.numel() for p in model.parameters() if p.requires_grad)
@@ -211,7 +385,8 @@ def main():
     # apps/vit/configs/cifar10.yaml: SGD lr 1e-2 momentum 0.9, grad_clip 1 — as the fused clip+SGD step over the flat
     # gradient arena (same arithmetic as clip_grad_norm_ + torch.optim.SGD; tests/test_model_gpu.py::test_fused_sgd_*)
     opt = build_optimizer(dp or model, "sgd", lr=1e-2, momentum=0.9, fused=not args.torch_sgd)
-    B = args.batch
+    B = per_rank_batch(args, world)
+    parity = dp_parity_check(ctx, model, dp, opt, B * world) if (dp is not None and not args.torch_sgd) else None
     g = torch.Generator().manual_seed(1234 + rank)
     n_host = 2  # distinct pinned host batches, alternated
     host = [(torch.randn(B, 3, 224, 224, generator=g).pin_memory(), torch.randint(0, 10, (B,), generator=g).pin_memory()) for _ in range(n_host)]
@@ -243,28 +418,12 @@ def main():
         loss, _ = train_step(dp or model, opt, [(x, y)], grad_clip=1.0, after_backward=after)
         return float(loss)  # D2H read of the step's result
 
-    def timed(fn_step, steps):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for i in range(steps):
-            fn_step(i)
-        e.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = torch.tensor([s.elapsed_time(e)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
     # ---- warm-up (untimed) ----
-    for i in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    for i in range(warm):
         step_resident(i)
     torch.cuda.synchronize()
 
@@ -273,14 +432,17 @@ def main():
         sampler.mark()
     _lib.reset_launch_count()
     _lib.GEMM_EVENTS = []
-    ms_total = timed(step_resident, args.steps)
+    ms_total = ctx.timed(step_resident, args.steps)
     launches = _lib.launch_count()
     gemm_events, _lib.GEMM_EVENTS = _lib.GEMM_EVENTS, None
     clocks = sampler.stop() if rank == 0 else None
     gemm_ms = sum(s.elapsed_time(e) for s, e, _ in gemm_events)
     gemm_flops = sum(f for _, _, f in gemm_events)
-    ms_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total / 1e3)
+    # the per-launch events cost host time in a step this short: `value` comes from a second timed run without them
+    ms_plain = ctx.timed(step_resident, args.steps)
+    ms_best = min(ms_total, ms_plain)
+    ms_step = ms_best / args.steps
+    value = world * B * args.steps / (ms_best / 1e3)
 
     # ---- timed: end to end from pinned host memory ----
     e2e = None
@@ -288,7 +450,7 @@ def main():
         for i in range(2):
             step_e2e(i, last=(i == 1))
         staged.clear()
-        ms_e2e = timed(lambda i: step_e2e(i, last=(i == args.steps - 1)), args.steps)
+        ms_e2e = ctx.timed(lambda i: step_e2e(i, last=(i == args.steps - 1)), args.steps)
         h2d = B * 3 * 224 * 224 * 4 + B * 8
         e2e = {"value": round(world * B * args.steps / (ms_e2e / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                "ms_per_step": round(ms_e2e / args.steps, 3)}
@@ -302,7 +464,6 @@ def main():
 
         pre = DevicePreprocessor(224, "train", dev)
         hu8 = [torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_host)]
-
         ustaged = {}
 
         def u_prep(i):
@@ -323,12 +484,12 @@ def main():
         for i in range(2):
             step_u8(i, last=(i == 1))
         ustaged.clear()
-        ms_u8 = timed(lambda i: step_u8(i, last=(i == args.steps - 1)), args.steps)
+        ms_u8 = ctx.timed(lambda i: step_u8(i, last=(i == args.steps - 1)), args.steps)
         pipe = {"value": round(world * B * args.steps / (ms_u8 / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": (B * 32 * 32 * 3 + B * 32) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": round(ms_u8 / args.steps, 3),
                 "source": "uint8 32x32x3 batch in pinned host memory; crop boxes / flips drawn on the host in torchvision's RNG order"}
 
-    # ---- secondary: plasticity estimator pairs/s (each rank takes its own shard of pairs; no collective) ----
+    # ---- secondary: plasticity estimator pairs/s, configs[0] shapes (each rank takes its own pairs; no collective) ----
     plast = None
     if args.pairs > 0:
         model.eval()
@@ -339,9 +500,7 @@ def main():
         for _ in range(2):
             est.squared_distances(dx1, dx2)
         reps = 5
-        ms_p = timed(lambda i: est.squared_distances(dx1, dx2), reps)
-        # end to end: the pair images start in pinned host memory; the next call's H2D copy runs on the side stream
-        # while the current call computes; the distance table is read back to the host every call
+        ms_p = ctx.timed(lambda i: est.squared_distances(dx1, dx2), reps)
         pstaged = {}
 
         def p_prefetch(i):
@@ -361,35 +520,48 @@ def main():
             return est.pair_distances(a, b)  # numpy on the host: D2H of the (1 + 5 n_layers) x P table
 
         p_step(0, True)
-        ms_pe = timed(lambda i: p_step(i, i == reps - 1), reps)
+        ms_pe = ctx.timed(lambda i: p_step(i, i == reps - 1), reps)
         pps = world * P * reps / (ms_p / 1e3)
+        gf = sweep_gflop(args.model, 1)
         plast = {"metric": f"ViT-{args.model[0].upper()}/16 plasticity pairs/s", "value": round(pps, 1), "unit": "pairs/s", "pairs_per_call": P,
                  "e2e": {"value": round(world * P * reps / (ms_pe / 1e3), 1), "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * 3 * 224 * 224 * 4 * world,
                          "d2h_bytes_per_step": (1 + 5 * len(model.model.blocks)) * P * 4 * world},
-                 "frac_of_tensor_peak": round(pps / world * PLAST_GFLOP_PER_PAIR.get(args.model, 0) / 1e3 / pk["bf16_tflops_sustained"], 4),
-                 "gflop_per_pair_executed": PLAST_GFLOP_PER_PAIR.get(args.model)}
+                 "roofline": {"bound": "tensor", "achieved": round(pps / world * gf["executed_per_pair"] / 1e3, 1), "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                              "frac": round(pps / world * gf["executed_per_pair"] / 1e3 / pk["bf16_tflops_sustained"], 4),
+                              "gflop_per_pair_executed": round(gf["executed_per_pair"], 3), "gflop_per_pair_reference_faithful": round(gf["reference_faithful_per_pair"], 3)}}
+        del est, dx1, dx2
         model.train()
 
+    # free the finetuning state before the ViT-L secondary block
+    del devb, host, staged
+    opt = dp = None
+    torch.cuda.empty_cache()
+    sweep = None
+    if args.sweep_images > 0:
+        try:
+            sweep = bench_sweep(ctx, args, model_name="large", images_total=args.sweep_images * world, secondary=True)
+        except Exception as exc:  # a secondary block must not take the headline down
+            sweep = {"error": repr(exc)[:300]}
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
-    # ---- CPU baseline (oracle port on the host cores; bounded sample) ----
+    # ---- CPU baseline: the unmodified reference on the host cores (bounded sample), N = 1 only ----
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, dt, cores = cpu_finetune_img_s(args.model, 8, 2, 1, comps)
-        cpu = {"value": round(v, 3), "unit": "img/s", "cores": cores, "kind": "port",
-               "sample": f"oracle port (torch fp32) of the same step at batch 8 (of 512), 2 timed steps after 1 warm-up, {dt:.2f} s/step"}
+        cpu, _ = cpu_reference_baseline(args.model, comps, steps=5, warmup=1, with_omp1=True, plasticity_pairs=64 if args.pairs > 0 else 0)
+    eager = None
+    if not args.no_gpu_eager and world == 1:
+        eager = gpu_eager_block(ctx, args, comps)
 
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
     traffic, traffic_src = ncu_traffic_per_launch()
     step_flops = 3 * FWD_GFLOP_PER_IMG.get(args.model, 0) * 1e9 * B if not comps else None
     out = {
         "metric": f"ViT-{args.model[0].upper()}/16 finetune img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": dict(workload_config(args.model, B, world, comps, n_trainable), l2="inputs>L2 (one step streams >30 GB)"),
+        "warmup": warm, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "strong" if (world > 1 and args.scaling == "strong") else "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": finetune_config(args.model, B, world, comps, n_trainable, args.scaling),
         "e2e": e2e, "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1) if achieved else None, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": round(achieved / pk["bf16_tflops_sustained"], 4) if achieved else None,
@@ -397,12 +569,140 @@ def main():
                      "flops_per_launch": round(gemm_flops / max(1, len(gemm_events))), "us_per_launch": round(gemm_ms * 1e3 / max(1, len(gemm_events)), 2),
                      "kernel": "gemm_tcgen05_kernel (all fwd/dgrad/wgrad launches of the timed steps, CUDA events per launch)", "peak_source": pk["source"] + " bf16_tflops_sustained",
                      "gemm_share_of_step": round(gemm_ms / ms_total, 4), "gemm_launches": len(gemm_events),
-                     "whole_step_frac": round(step_flops * args.steps / (ms_total / 1e3) / 1e12 / pk["bf16_tflops_sustained"], 4) if step_flops else None},
-        "cpu_baseline": cpu, "clocks": clocks, "plasticity": plast, "e2e_u8_input_pipeline": pipe,
+                     "whole_step_frac": round(step_flops * args.steps / (ms_best / 1e3) / 1e12 / pk["bf16_tflops_sustained"], 4) if step_flops else None},
+        "cpu_baseline": cpu, "clocks": clocks, "dp_parity": parity, "plasticity": plast, "sweep": sweep, "e2e_u8_input_pipeline": pipe, "gpu_eager": eager,
+        "ms_per_step_with_per_launch_events": round(ms_total / args.steps, 3),
     }
     print(json.dumps(out))
+
+
+def gpu_eager_block(ctx, args, comps):
+    """Informational (SURVEY.md 8d 'GPU baseline'): the reference's own modules, eager, on this same GPU at the same batch —
+    fp32 as shipped (TF32 off) and under torch.autocast(bfloat16). Not the reference arm (that one is the CPU path)."""
+    torch = ctx.torch
+    from baseline import reference_arm as R
+
+    if R.available() is not None:
+        return {"unavailable": R.available()}
+    out = {}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    for name, autocast in (("fp32", False), ("autocast_bf16", True)):
+        try:
+            torch.cuda.empty_cache()
+            v, dt, _ = R.finetune(args.model, args.batch, 3, 1, comps, os.cpu_count() or 1, device=str(ctx.dev), autocast=autocast)
+            out[name] = {"value": round(v, 1), "unit": "img/s", "ms_per_step": round(dt * 1e3, 2), "batch": args.batch}
+        except Exception as exc:  # e.g. out of memory: the reference materialises two fp32 score tensors per layer
+            out[name] = {"error": repr(exc)[:200]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def bench_sweep(ctx, args, model_name: str, images_total: int, secondary: bool = False):
+    """BASELINE.json configs[4]: ViT-L/16, `images_total` images x the eps grid, sharded over the ranks."""
+    torch, dist = ctx.torch, ctx.dist
+    from vit_plasticity_b200 import _lib
+    from vit_plasticity_b200.distributed import shard_range
+    from vit_plasticity_b200.plasticity import PlasticityEstimator, gather_tables, sweep_local
+    from vit_plasticity_b200.preprocess import DevicePreprocessor
+
+    rank, world, dev, pk = ctx.rank, ctx.world, ctx.dev, ctx.pk
+    eps = [float(e) for e in args.eps.split(",")]
+    ppc = 64
+    model = build_vit(ctx, model_name).eval()
+    est = PlasticityEstimator(model)
+    lo, hi = shard_range(images_total, rank, world)
+    n_local = hi - lo
+    # resident fp32 images of this rank's shard (seeded per image block, so the data does not depend on the sharding)
+    x_dev = torch.empty(n_local, 3, 224, 224, device=dev)
+    gen = torch.Generator(device=dev)
+    for s0 in range(0, n_local, 256):
+        gen.manual_seed(7_000_000 + lo + s0)
+        x_dev[s0 : s0 + 256].normal_(generator=gen)
+    # warm-up: one chunk through every kernel of the path
+    for _ in range(max(1, min(args.warmup, 3))):
+        est.sweep_squared_distances(x_dev[: min(ppc, n_local)], x_dev[: min(ppc, n_local)].flip(0), eps)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(ctx.local)
+    if rank == 0 and not secondary:
+        sampler.start()
+        sampler.mark()
+    _lib.reset_launch_count()
+    result = {}
+
+    def run_resident(_i):
+        result["t"] = sweep_local(est, x_dev, eps, noise_seed=11, first_image=lo, pairs_per_call=ppc)  # [n_eps, rows, n_local] on the device
+
+    ms = ctx.timed(run_resident, 1)
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if (rank == 0 and not secondary) else None
+    # ---- the only collective: ONE gather of the distance tables, outside the device-timed region, timed on its own ----
+    gather_s = None
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        table = gather_tables(result["t"], images_total, (images_total + world - 1) // world)
+        torch.cuda.synchronize()
+        gather_s = time.perf_counter() - t0
+        if rank == 0:
+            assert table.shape == (len(eps), len(est.keys()), images_total)
+    n_pairs = images_total * len(eps)
+    value = n_pairs / (ms / 1e3)
+    # ---- end to end: the shard starts as uint8 CIFAR-shaped samples in pinned host memory, the reference's "test" transform
+    # (Resize 224 + ToTensor + Normalize) runs on the device, the distance table is read back to the host ----
+    e2e = None
+    if not args.no_e2e:
+        gcpu = torch.Generator().manual_seed(1000 + rank)
+        hu8 = torch.randint(0, 256, (n_local, 32, 32, 3), dtype=torch.uint8, generator=gcpu).pin_memory()
+        pre = DevicePreprocessor(224, "test", dev)
+        sweep_local(est, hu8[: min(ppc, n_local)], eps, 11, lo, ppc, pre).cpu()
+        ms_e = ctx.timed(lambda _i: sweep_local(est, hu8, eps, 11, lo, ppc, pre).cpu(), 1)  # .cpu(): D2H of this rank's table
+        n_rows = 1 + 5 * len(model.model.blocks)
+        e2e = {"value": round(n_pairs / (ms_e / 1e3), 1), "unit": "pairs/s", "h2d_bytes_per_step": images_total * 32 * 32 * 3,
+               "d2h_bytes_per_step": n_rows * images_total * len(eps) * 4, "seconds": round(ms_e / 1e3, 3),
+               "source": "uint8 32x32x3 samples in pinned host memory -> device-side Resize/ToTensor/Normalize (bit-exact vs torchvision) -> estimator -> distance table on the host"}
+    gf = sweep_gflop(model_name, len(eps))
+    achieved = value / world * gf["executed_per_pair"] / 1e3
+    out = {"metric": f"ViT-{model_name[0].upper()}/16 plasticity sweep pairs/s", "value": round(value, 1), "unit": "pairs/s", "n_gpus": world,
+           "images": images_total, "eps": eps, "pairs": n_pairs, "seconds": round(ms / 1e3, 3), "gather_seconds": round(gather_s, 4) if gather_s is not None else None,
+           "e2e": e2e, "gpu_launches": launches,
+           "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4),
+                        "gflop_per_pair_executed": round(gf["executed_per_pair"], 3), "gflop_per_pair_reference_faithful": round(gf["reference_faithful_per_pair"], 3),
+                        "reference_faithful_tflops_equivalent": round(value / world * gf["reference_faithful_per_pair"] / 1e3, 1),
+                        "note": "achieved = executed FLOPs (f(x) and everything linear in the noise shared by the eps grid) / device time; peak = measured sustained bf16"}}
+    if clocks is not None:
+        out["clocks"] = clocks
+    del x_dev, est, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    ctx = Ctx()
+    try:
+        if args.workload == "sweep":
+            eps = [float(e) for e in args.eps.split(",")]
+            out = bench_sweep(ctx, args, args.model, args.images)
+            if ctx.rank == 0:
+                out.update({"steps": args.steps, "warmup": args.warmup, "ms_per_step": round(out["seconds"] * 1e3, 1), "higher_is_better": True, "scaling": "strong",
+                            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": sweep_config(args.model, args.images, eps, ctx.world, 64)})
+                if not args.no_cpu_baseline and ctx.world == 1:
+                    from baseline import reference_arm as R
+
+                    if R.available() is None:
+                        cores = os.cpu_count() or 1
+                        v, dt = R.plasticity(args.model, 4, 2, cores)
+                        out["cpu_baseline"] = {"value": round(v, 4), "unit": "pairs/s", "cores": cores, "kind": "reference",
+                                               "sample": f"unmodified reference estimator on 4 ViT-{args.model}/16 pairs, fp32, {cores} threads, {dt:.1f} s"}
+                print(json.dumps(out))
+        else:
+            bench_finetune(ctx, args)
+    finally:
+        ctx.close()
 
 
 if __name__ == "__main__":

@@ -26,7 +26,7 @@ def expm1_kernel(w):
     """what the kernel evaluates: a 4th-order Taylor polynomial below 1/8, exp2 - 1 above"""
     poly = w * (1 + w * (0.5 + w * (1 / 6 + w * (1 / 24))))
     big = torch.exp2(w * 1.4426950408889634) - 1
-    return torch.where(w.abs() < 0.125, poly, big)
+    return torch.where(w > -0.125, poly, big)
 
 
 def delta_path(e32, d32, wqkv, bqkv, wo, h):
@@ -46,10 +46,10 @@ def delta_path(e32, d32, wqkv, bqkv, wo, h):
     mw = dS.max(-1, keepdim=True).values
     g = pa * expm1_kernel((dS - mw) * c)
     dl = g.sum(-1, keepdim=True)
-    pa16, g16 = bf(pa), bf(g)
-    Na = pa16 @ va
-    GQ = g16 @ va + g16 @ dv + pa16 @ dv
-    D = (GQ - (dl / la) * Na) / (la + dl)
+    lb = (pa + g).sum(-1, keepdim=True)
+    H = bf((g - (dl / la) * pa) / lb)  # P_b - P_a formed in fp32, then ONE bf16 rounding
+    Pa = bf(pa / la)
+    D = H @ va + H @ dv + Pa @ dv
     D = bf(D).transpose(1, 2).reshape(e32.shape)
     out = D @ bf(wo).T
     return (out ** 2).flatten(1).sum(-1).sqrt()

@@ -402,12 +402,14 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
 //   dS  = q dk^T + dq k^T + dq dk^T  (= S_b - S)  (3 x SS MMA into one accumulator) -> buffer B
 //   p   = exp2((S - rowmax S) c),  l = sum p
 //   g   = p * expm1((dS - rowmax dS) / 8)         (the softmax is shift invariant per row: the row max removes the
-//                                                  common mode of dS; expm1 by a polynomial below 1/8, so p_b - p = g
-//                                                  keeps full relative precision however small dS is)
-//   dl  = sum g,  lb = sum (p + g)                (un-normalised: P_b = (p + g) / lb, P_a = p / l)
-//   Na  = p v,  GQ = g v + g dv + p dv            (TS MMAs: p and g packed to bf16 over buffer A, accumulators over B)
-//   out = O_b - O_a = (GQ - (dl / l) Na) / lb     fp32, one bf16 rounding
-// Exact for any perturbation size (tools/emulate_delta_attention.py: <= 1.2e-3 of the fp64 value from |d|/|a| = 1e-4 to 10).
+//                                                  common mode of dS; expm1 by a polynomial above -1/8, so p_b - p = g
+//                                                  keeps full relative precision however small dS is). g is parked in
+//                                                  fp32 over the dS columns it came from until the row sums are known.
+//   dl  = sum g,  lb = sum (p + g)                (P_a = p / l,  P_b = (p + g) / lb)
+//   H   = P_b - P_a = (g - (dl / l) p) / lb       fp32, THEN one bf16 rounding: relative precision at any perturbation size
+//   out = O_b - O_a = H v + H dv + P_a dv         (TS MMAs: P_a and H packed to bf16 over buffer A, accumulator over B)
+// Uniformly accurate (tools/emulate_delta_attention.py: <= 3e-3 of the fp64 difference per layer and <= 5e-3 per token row
+// from |d| / |a| = 1e-4 to 40, where the perturbed softmax is one-hot on a key that had negligible weight before).
 // One unit (128 query rows) at a time: TMEM holds S (208) + dS (208) columns, so units are not double-buffered; the
 // Q/K and V operand groups have their own barriers, so the next item's Q/K load overlaps this item's softmax and P V.
 constexpr int D_OFF_QA = 0, D_OFF_KA = OPER_BYTES, D_OFF_DQ = 2 * OPER_BYTES, D_OFF_DK = 3 * OPER_BYTES, D_OFF_VA = 4 * OPER_BYTES,
@@ -415,7 +417,7 @@ constexpr int D_OFF_QA = 0, D_OFF_KA = OPER_BYTES, D_OFF_DQ = 2 * OPER_BYTES, D_
 constexpr int D_EXCH_FLOATS = 4 * 128;  // one value per (column part, row)
 constexpr int D_SMEM = 6 * OPER_BYTES + 5 * D_EXCH_FLOATS * 4 + 256 + 1024;
 static_assert(D_SMEM <= 232448, "shared memory budget");
-constexpr uint32_t D_COL_A = 0, D_COL_G = 104, D_COL_B = 208, D_COL_NA = 224, D_COL_GQ = 288;
+constexpr uint32_t D_COL_A = 0, D_COL_H = 104, D_COL_B = 208, D_COL_ACC = 224;
 
 // exp(w) - 1 for w <= 0: 4th-order polynomial above -1/8 (truncation 3e-7 relative), exp2 - 1 below
 __device__ __forceinline__ float expm1_neg(float w) {
@@ -424,8 +426,8 @@ __device__ __forceinline__ float expm1_neg(float w) {
     return w > -0.125f ? poly : big;
 }
 
-// One row's share of a unit: NC (64 or 48) columns starting at cbeg. Leaves packed bf16 p at buffer-A columns
-// [cbeg / 2, +NC / 2) and packed g at [104 + cbeg / 2, +NC / 2), and the row's partial sums in the exchange arrays.
+// One row's share of a unit: NC (64 or 48) columns starting at cbeg. Leaves packed bf16 P_a at buffer-A columns
+// [cbeg / 2, +NC / 2) and packed H at [104 + cbeg / 2, +NC / 2).
 template <int NC>
 __device__ __forceinline__ void delta_softmax_part(uint32_t lane_addr, int cbeg, int nvalid, float* sMaxA, float* sMaxW, float* sSumA,
                                                    float* sSumG, float* sSumB, int part, int row, int quarter) {
@@ -462,69 +464,78 @@ __device__ __forceinline__ void delta_softmax_part(uint32_t lane_addr, int cbeg,
     m = fmaxf(fmaxf(sMaxA[row], sMaxA[128 + row]), fmaxf(sMaxA[256 + row], sMaxA[384 + row]));  // column 0 is valid: finite
     mw = fmaxf(fmaxf(sMaxW[row], sMaxW[128 + row]), fmaxf(sMaxW[256 + row], sMaxW[384 + row]));
     const float mc = m * c;
-    // ---- p = exp2((S - m) c), kept in fp32 in the registers that held S; packed bf16 copy -> buffer A ----
+    // ---- p = exp2((S - m) c), kept in fp32 in the registers that held S ----
     float la = 0.f;
-    {
-        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float a = (2 * i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v0[2 * i]), c, -mc)) : 0.f;
-            const float b = (2 * i + 1 < nvalid) ? fast_ex2(fmaf(__uint_as_float(v0[2 * i + 1]), c, -mc)) : 0.f;
-            v0[2 * i] = __float_as_uint(a);
-            v0[2 * i + 1] = __float_as_uint(b);
-            pk[i] = pack_bf16x2(a, b);
-            la += a + b;
-        }
-        tmem_st_x16(lane_addr + D_COL_A + (cbeg >> 1), pk);
+    for (int i = 0; i < 32; ++i) {
+        const float a = (i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v0[i]), c, -mc)) : 0.f;
+        v0[i] = __float_as_uint(a);
+        la += a;
     }
-    {
-        uint32_t pk[(NC - 32) / 2];
 #pragma unroll
-        for (int i = 0; i < (NC - 32) / 2; ++i) {
-            const float a = (32 + 2 * i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v1[2 * i]), c, -mc)) : 0.f;
-            const float b = (32 + 2 * i + 1 < nvalid) ? fast_ex2(fmaf(__uint_as_float(v1[2 * i + 1]), c, -mc)) : 0.f;
-            v1[2 * i] = __float_as_uint(a);
-            v1[2 * i + 1] = __float_as_uint(b);
-            pk[i] = pack_bf16x2(a, b);
-            la += a + b;
-        }
-        if constexpr (NC == 64)
-            tmem_st_x16(lane_addr + D_COL_A + (cbeg >> 1) + 16, pk);
-        else
-            tmem_st_x8(lane_addr + D_COL_A + (cbeg >> 1) + 16, pk);
+    for (int i = 0; i < NC - 32; ++i) {
+        const float a = (32 + i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v1[i]), c, -mc)) : 0.f;
+        v1[i] = __float_as_uint(a);
+        la += a;
     }
-    // ---- g = p * expm1((dS - mw) / 8): second pass over the dS columns, 16 at a time ----
+    // ---- g = p * expm1((dS - mw) / 8), parked in fp32 over the dS columns it came from (this thread's own columns) ----
     const float mw8 = mw * 0.125f;
     float dl = 0.f, lb = 0.f;
-    auto piece = [&](auto& pv, int base, int col) {  // pv[base .. base + 16) hold p of columns [col, col + 16) of this part
-        uint32_t w[16], pk[8];
+    auto make_g = [&](auto& pv, int base, int col) {  // pv[base .. base + 16) hold p of columns [col, col + 16) of this part
+        uint32_t w[16];
+        tmem_ld_32x32b_x16(lane_addr + D_COL_B + cbeg + col, w);
+        tmem_ld_wait();
+        reg_fence(w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float p0 = __uint_as_float(pv[base + i]);
+            // the clamp keeps masked columns (p = 0, dS = 0 there) at expm1(0) = 0 instead of 0 * inf
+            const float g0 = p0 * expm1_neg(fminf(fmaf(__uint_as_float(w[i]), 0.125f, -mw8), 0.f));
+            w[i] = __float_as_uint(g0);
+            dl += g0;
+            lb += p0 + g0;
+        }
+        tmem_st_x16(lane_addr + D_COL_B + cbeg + col, w);
+    };
+    make_g(v0, 0, 0);
+    make_g(v0, 16, 16);
+    make_g(v1, 0, 32);
+    if constexpr (NC == 64) make_g(v1, 16, 48);
+    sSumA[part * 128 + row] = la;
+    sSumG[part * 128 + row] = dl;
+    sSumB[part * 128 + row] = lb;
+    tmem_st_wait();  // g is re-read below by this same thread
+    named_bar_sync(5 + quarter, 128);
+    la = (sSumA[row] + sSumA[128 + row]) + (sSumA[256 + row] + sSumA[384 + row]);
+    dl = (sSumG[row] + sSumG[128 + row]) + (sSumG[256 + row] + sSumG[384 + row]);
+    lb = (sSumB[row] + sSumB[128 + row]) + (sSumB[256 + row] + sSumB[384 + row]);
+    const float inv_la = 1.f / la, inv_lb = 1.f / fmaxf(lb, 1e-37f);
+    const float rho = dl * inv_la;
+    // ---- P_a = p / la and H = (g - rho p) / lb, packed to bf16 over buffer A (every S column of this quarter is in
+    //      registers since the first barrier) ----
+    auto pack_h = [&](auto& pv, int base, int col) {
+        uint32_t w[16], pa[8], ph[8];
         tmem_ld_32x32b_x16(lane_addr + D_COL_B + cbeg + col, w);
         tmem_ld_wait();
         reg_fence(w);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float p0 = __uint_as_float(pv[base + 2 * i]), p1 = __uint_as_float(pv[base + 2 * i + 1]);
-            // the clamp keeps masked columns (p = 0, dS = 0 there) at expm1(0) = 0 instead of 0 * inf
-            const float g0 = p0 * expm1_neg(fminf(fmaf(__uint_as_float(w[2 * i]), 0.125f, -mw8), 0.f));
-            const float g1 = p1 * expm1_neg(fminf(fmaf(__uint_as_float(w[2 * i + 1]), 0.125f, -mw8), 0.f));
-            pk[i] = pack_bf16x2(g0, g1);
-            dl += g0 + g1;
-            lb += (p0 + g0) + (p1 + g1);
+            pa[i] = pack_bf16x2(p0 * inv_la, p1 * inv_la);
+            ph[i] = pack_bf16x2(fmaf(-rho, p0, __uint_as_float(w[2 * i])) * inv_lb, fmaf(-rho, p1, __uint_as_float(w[2 * i + 1])) * inv_lb);
         }
-        tmem_st_x8(lane_addr + D_COL_G + ((cbeg + col) >> 1), pk);
+        tmem_st_x8(lane_addr + D_COL_A + ((cbeg + col) >> 1), pa);
+        tmem_st_x8(lane_addr + D_COL_H + ((cbeg + col) >> 1), ph);
     };
-    piece(v0, 0, 0);
-    piece(v0, 16, 16);
-    piece(v1, 0, 32);
-    if constexpr (NC == 64) piece(v1, 16, 48);
-    sSumA[part * 128 + row] = la;
-    sSumG[part * 128 + row] = dl;
-    sSumB[part * 128 + row] = lb;
+    pack_h(v0, 0, 0);
+    pack_h(v0, 16, 16);
+    pack_h(v1, 0, 32);
+    if constexpr (NC == 64) pack_h(v1, 16, 48);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
 attention_perturb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD, bf16* __restrict__ out, int L,
-                       int H, int batch, int n_items) {
+                         int H, int batch, int n_items) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     float* sMaxA = reinterpret_cast<float*>(smem + 6 * OPER_BYTES);  // [4][128] each
@@ -607,7 +618,7 @@ attention_perturb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int u = 0; u < U; ++u) {
             const int n = u >> 1, t = u & 1;
             if (t == 0) mbar_wait(full_qk, n & 1, 82);
-            mbar_wait(o_free, (u & 1) ^ 1, 83);  // the accumulators of unit u-1 (over buffer B) have been read out
+            mbar_wait(o_free, (u & 1) ^ 1, 83);  // the accumulator of unit u-1 (over buffer B) has been read out
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t qa = (smem_lo + ((D_OFF_QA + t * TILE_BYTES) >> 4)) | LBO_K;
@@ -634,16 +645,13 @@ attention_perturb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 13; ++k)  // 16 keys per step = 8 packed columns
-                    umma_bf16_ts(tmem_base + D_COL_NA, tmem_base + D_COL_A + k * 8, make_desc(va + k * 128, DESC_HI), idesc_o, k > 0);
+                    umma_bf16_ts(tmem_base + D_COL_ACC, tmem_base + D_COL_H + k * 8, make_desc(va + k * 128, DESC_HI), idesc_o, k > 0);
 #pragma unroll
                 for (int k = 0; k < 13; ++k)
-                    umma_bf16_ts(tmem_base + D_COL_GQ, tmem_base + D_COL_G + k * 8, make_desc(va + k * 128, DESC_HI), idesc_o, k > 0);
+                    umma_bf16_ts(tmem_base + D_COL_ACC, tmem_base + D_COL_H + k * 8, make_desc(dv + k * 128, DESC_HI), idesc_o, 1);
 #pragma unroll
                 for (int k = 0; k < 13; ++k)
-                    umma_bf16_ts(tmem_base + D_COL_GQ, tmem_base + D_COL_G + k * 8, make_desc(dv + k * 128, DESC_HI), idesc_o, 1);
-#pragma unroll
-                for (int k = 0; k < 13; ++k)
-                    umma_bf16_ts(tmem_base + D_COL_GQ, tmem_base + D_COL_A + k * 8, make_desc(dv + k * 128, DESC_HI), idesc_o, 1);
+                    umma_bf16_ts(tmem_base + D_COL_ACC, tmem_base + D_COL_A + k * 8, make_desc(dv + k * 128, DESC_HI), idesc_o, 1);
                 umma_commit(o_ready);
                 if (t == 1) umma_commit(empty_v);
             }
@@ -669,37 +677,27 @@ attention_perturb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
-            // ---- read the two accumulators out (16 of the 64 output columns per warp) ----
+            // ---- read the accumulator out (16 of the 64 output columns per warp): it already holds O_b - O_a ----
             mbar_wait(o_ready, u & 1, 87);
             tc_fence_after();
-            uint32_t na[16], gq[16];
-            tmem_ld_32x32b_x16(lane_addr + D_COL_NA + part * 16, na);
-            tmem_ld_32x32b_x16(lane_addr + D_COL_GQ + part * 16, gq);
-            // o_ready implies every warp arrived on p_ready, i.e. wrote its partial sums before (release / acquire chain)
-            const float la = (sSumA[row] + sSumA[128 + row]) + (sSumA[256 + row] + sSumA[384 + row]);
-            const float dl = (sSumG[row] + sSumG[128 + row]) + (sSumG[256 + row] + sSumG[384 + row]);
-            const float lb = (sSumB[row] + sSumB[128 + row]) + (sSumB[256 + row] + sSumB[384 + row]);
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(lane_addr + D_COL_ACC + part * 16, o);
             tmem_ld_wait();
-            reg_fence(na);
-            reg_fence(gq);
+            reg_fence(o);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(o_free);
             const int q = t * 128 + row;
             if (q < L) {
-                const float ratio = dl / la, inv = 1.f / fmaxf(lb, 1e-37f);
-                float r[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = fmaf(-ratio, __uint_as_float(na[i]), __uint_as_float(gq[i])) * inv;
                 uint4 w0, w1;
-                w0.x = pack_bf16x2(r[0], r[1]);
-                w0.y = pack_bf16x2(r[2], r[3]);
-                w0.z = pack_bf16x2(r[4], r[5]);
-                w0.w = pack_bf16x2(r[6], r[7]);
-                w1.x = pack_bf16x2(r[8], r[9]);
-                w1.y = pack_bf16x2(r[10], r[11]);
-                w1.z = pack_bf16x2(r[12], r[13]);
-                w1.w = pack_bf16x2(r[14], r[15]);
+                w0.x = pack_bf16x2(__uint_as_float(o[0]), __uint_as_float(o[1]));
+                w0.y = pack_bf16x2(__uint_as_float(o[2]), __uint_as_float(o[3]));
+                w0.z = pack_bf16x2(__uint_as_float(o[4]), __uint_as_float(o[5]));
+                w0.w = pack_bf16x2(__uint_as_float(o[6]), __uint_as_float(o[7]));
+                w1.x = pack_bf16x2(__uint_as_float(o[8]), __uint_as_float(o[9]));
+                w1.y = pack_bf16x2(__uint_as_float(o[10]), __uint_as_float(o[11]));
+                w1.z = pack_bf16x2(__uint_as_float(o[12]), __uint_as_float(o[13]));
+                w1.w = pack_bf16x2(__uint_as_float(o[14]), __uint_as_float(o[15]));
                 uint4* dst = reinterpret_cast<uint4*>(out + (((int64_t)layer * batch + b) * L + q) * E + hd * HD + part * 16);
                 dst[0] = w0;
                 dst[1] = w1;

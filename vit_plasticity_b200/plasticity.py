@@ -234,17 +234,38 @@ def sweep_noise(n_images: int, image_shape, noise_seed: int, first_image: int, d
     return L.philox_normal(n_images, tuple(image_shape), noise_seed, first_image, device)
 
 
+def sweep_local(est: PlasticityEstimator, images, eps_list, noise_seed: int = 0, first_image: int = 0, pairs_per_call: int = 64,
+                transform=None, device=None) -> torch.Tensor:
+    """Distances of the pairs (x_i, x_i + eps n_i) for the images of ONE shard: f32 device tensor
+    [n_eps, 1 + 5 n_layers, n_images]. ``first_image`` is the global index of ``images[0]`` (the noise n_i is keyed by the
+    global image index). x + eps n is never formed: the pair is carried as (x, eps n), f(x) and everything linear in n are
+    shared by the whole eps grid."""
+    dev = device if device is not None else next(est.net.parameters()).device
+    eps_list = [float(e) for e in eps_list]
+    chunks: list[torch.Tensor] = []
+    n = images.shape[0]
+    for s0 in range(0, n, pairs_per_call):
+        s1 = min(s0 + pairs_per_call, n)
+        x = images[s0:s1].to(dev, non_blocking=True)
+        x = transform(x) if transform is not None else x.float()
+        noise = sweep_noise(s1 - s0, x.shape[1:], noise_seed, first_image + s0, dev)
+        chunks.append(torch.stack(est.sweep_squared_distances(x, noise, eps_list), 0).sqrt())  # [n_eps, rows, n_chunk]
+    return torch.cat(chunks, 2) if chunks else torch.zeros(len(eps_list), len(est.keys()), 0, device=dev)
+
+
 def perturbation_sweep(model, images, eps_list, noise_seed: int = 0, pairs_per_call: int = 64, rank: int | None = None,
-                       world: int | None = None, group=None, estimator: "PlasticityEstimator | None" = None, stats: dict | None = None):
+                       world: int | None = None, group=None, estimator: "PlasticityEstimator | None" = None, stats: dict | None = None,
+                       transform=None):
     """Plasticity under input perturbations of growing magnitude (BASELINE.json configs[4]): pairs (x, x + eps * n),
     n ~ N(0, 1) per image from ``noise_seed`` (:func:`sweep_noise`), for every eps in ``eps_list``.
 
     The N images are sharded contiguously over the ranks (each pair is independent: apps/vit/analysis.py:68 reduces per
-    sample); every rank streams its shard from ``images`` (host or device, fp32 NCHW) through the fused estimator:
-    x + eps * n is never formed — the pair is carried as (x, eps * n), f(x) and everything linear in n are shared by the
-    whole eps grid — and only the (1 + 5 n_layers) x N_local distance table per eps leaves the GPU. No collective on
-    the data path; rank 0 receives {eps: {key: (N,) float32}} from ONE gather at the end, the other ranks get None.
-    ``stats`` (optional dict) receives ``gather_s``, the wall time of that gather.
+    sample); every rank streams its shard from ``images`` (host or device, fp32 NCHW) through :func:`sweep_local`, and only
+    the (1 + 5 n_layers) x N_local distance table per eps leaves the GPU. No collective on the data path; rank 0 receives
+    {eps: {key: (N,) float32}} from ONE gather at the end, the other ranks get None.
+    ``stats`` (optional dict) receives ``gather_s``, the wall time of that gather. ``transform`` (optional callable) maps a
+    chunk of ``images`` already on the device to fp32 NCHW — e.g. ``preprocess.DevicePreprocessor(224, "test")`` when
+    ``images`` holds the dataset's raw uint8 HWC samples, so only those cross PCIe.
     """
     import time
 
@@ -255,16 +276,9 @@ def perturbation_sweep(model, images, eps_list, noise_seed: int = 0, pairs_per_c
     est = estimator if estimator is not None else PlasticityEstimator(model)
     n_total = images.shape[0]
     lo, hi = shard_range(n_total, rank, world)
-    dev = next(_inner(model).parameters()).device
     eps_list = [float(e) for e in eps_list]
     keys = est.keys()
-    chunks: list[torch.Tensor] = []
-    for s0 in range(lo, hi, pairs_per_call):
-        s1 = min(s0 + pairs_per_call, hi)
-        x = images[s0:s1].to(dev, non_blocking=True).float()
-        noise = sweep_noise(s1 - s0, x.shape[1:], noise_seed, s0, dev)
-        chunks.append(torch.stack(est.sweep_squared_distances(x, noise, eps_list), 0).sqrt())  # [n_eps, rows, n_chunk]
-    local = torch.cat(chunks, 2) if chunks else torch.zeros(len(eps_list), len(keys), 0, device=dev)
+    local = sweep_local(est, images[lo:hi], eps_list, noise_seed, lo, pairs_per_call, transform, next(_inner(model).parameters()).device)
     distributed = dist.is_available() and dist.is_initialized() and (world is None or world == dist.get_world_size(group))
     t0 = time.perf_counter()
     if distributed and dist.get_world_size(group) > 1:
