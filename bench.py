@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the informational block: reference modules eager on the same GPU")
     ap.add_argument("--torch-sgd", action="store_true", help="clip_grad_norm_ + torch.optim.SGD instead of the fused arena step")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel of the step from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.model is None:
         args.model = "large" if args.workload == "sweep" else "base"
@@ -372,7 +373,7 @@ def bench_finetune(ctx, args):
     torch, dist = ctx.torch, ctx.dist
     from vit_plasticity_b200 import _lib
     from vit_plasticity_b200.distributed import DataParallel
-    from vit_plasticity_b200.finetune import build_optimizer, freeze_model, train_step
+    from vit_plasticity_b200.finetune import GraphedTrainStep, build_optimizer, freeze_model, train_step
     from vit_plasticity_b200.plasticity import PlasticityEstimator
 
     rank, world, dev, pk = ctx.rank, ctx.world, ctx.dev, ctx.pk
@@ -392,9 +393,18 @@ def bench_finetune(ctx, args):
     host = [(torch.randn(B, 3, 224, 224, generator=g).pin_memory(), torch.randint(0, 10, (B,), generator=g).pin_memory()) for _ in range(n_host)]
     devb = [(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)) for x, y in host]
     after = dp.finish_grad_sync if dp is not None else None
+    use_graph = not (args.no_graph or args.torch_sgd)
+    # the public API for fixed-shape training: the whole step (forward, loss, backward, bucket all-reduces, clip + SGD,
+    # arena reset) captured once and replayed — one graph launch per step instead of ~300 launches from Python
+    graphed = GraphedTrainStep(dp or model, opt, grad_clip=1.0, after_backward=after) if use_graph else None
+
+    def step_eager(i):
+        return train_step(dp or model, opt, [devb[i % n_host]], grad_clip=1.0, after_backward=after)
 
     def step_resident(i):
-        return train_step(dp or model, opt, [devb[i % n_host]], grad_clip=1.0, after_backward=after)
+        if graphed is not None:
+            return graphed([devb[i % n_host]])
+        return step_eager(i)
 
     copy_stream = torch.cuda.Stream()
     staged = {}
@@ -415,34 +425,38 @@ def bench_finetune(ctx, args):
         y.record_stream(torch.cuda.current_stream())
         if not last:
             prefetch(i + 1)
-        loss, _ = train_step(dp or model, opt, [(x, y)], grad_clip=1.0, after_backward=after)
+        if graphed is not None:
+            loss, _ = graphed([(x, y)])
+        else:
+            loss, _ = train_step(dp or model, opt, [(x, y)], grad_clip=1.0, after_backward=after)
         return float(loss)  # D2H read of the step's result
 
     sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
-    # ---- warm-up (untimed) ----
+    # ---- warm-up (untimed): the first call is eager, the second captures the graph ----
     warm = max(3, args.warmup)
     for i in range(warm):
         step_resident(i)
     torch.cuda.synchronize()
 
-    # ---- timed: inputs resident in HBM; GEMM launches individually event-timed for the roofline ----
+    # ---- timed: inputs resident in HBM ----
     if rank == 0:
         sampler.mark()
     _lib.reset_launch_count()
-    _lib.GEMM_EVENTS = []
-    ms_total = ctx.timed(step_resident, args.steps)
-    launches = _lib.launch_count()
-    gemm_events, _lib.GEMM_EVENTS = _lib.GEMM_EVENTS, None
+    ms_best = ctx.timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in gemm_events)
-    gemm_flops = sum(f for _, _, f in gemm_events)
-    # the per-launch events cost host time in a step this short: `value` comes from a second timed run without them
-    ms_plain = ctx.timed(step_resident, args.steps)
-    ms_best = min(ms_total, ms_plain)
+    launches = graphed.launches_per_step * args.steps if graphed is not None else _lib.launch_count()
     ms_step = ms_best / args.steps
     value = world * B * args.steps / (ms_best / 1e3)
+    # ---- the same steps issued kernel by kernel, every GEMM launch bracketed by CUDA events on its stream (roofline) ----
+    for i in range(2):
+        step_eager(i)
+    _lib.GEMM_EVENTS = []
+    ms_total = ctx.timed(step_eager, args.steps)
+    gemm_events, _lib.GEMM_EVENTS = _lib.GEMM_EVENTS, None
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f in gemm_events)
 
     # ---- timed: end to end from pinned host memory ----
     e2e = None
@@ -465,6 +479,7 @@ def bench_finetune(ctx, args):
         pre = DevicePreprocessor(224, "train", dev)
         hu8 = [torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_host)]
         ustaged = {}
+        graphed_u8 = GraphedTrainStep(dp or model, opt, grad_clip=1.0, after_backward=after) if use_graph else None
 
         def u_prep(i):
             # host side of the next batch (crop boxes / flips in torchvision's draw order, 1.5 MB uint8 copy) while the
@@ -476,13 +491,16 @@ def bench_finetune(ctx, args):
                 u_prep(i)
             xu8, params = ustaged.pop(i)
             x = pre.patches(xu8, params)
-            loss, _ = train_step(dp or model, opt, [(x, devb[i % n_host][1])], grad_clip=1.0, after_backward=after)
+            if graphed_u8 is not None:
+                loss, _ = graphed_u8([(x, devb[i % n_host][1])])
+            else:
+                loss, _ = train_step(dp or model, opt, [(x, devb[i % n_host][1])], grad_clip=1.0, after_backward=after)
             if not last:
                 u_prep(i + 1)
             return float(loss)
 
-        for i in range(2):
-            step_u8(i, last=(i == 1))
+        for i in range(3):
+            step_u8(i, last=(i == 2))
         ustaged.clear()
         ms_u8 = ctx.timed(lambda i: step_u8(i, last=(i == args.steps - 1)), args.steps)
         pipe = {"value": round(world * B * args.steps / (ms_u8 / 1e3), 2), "unit": "img/s", "h2d_bytes_per_step": (B * 32 * 32 * 3 + B * 32) * world,
@@ -534,6 +552,8 @@ def bench_finetune(ctx, args):
 
     # free the finetuning state before the ViT-L secondary block
     del devb, host, staged
+    graph_info = {"used": graphed is not None, "launches_per_step": graphed.launches_per_step if graphed is not None else None}
+    graphed = graphed_u8 = None
     opt = dp = None
     torch.cuda.empty_cache()
     sweep = None
@@ -569,9 +589,10 @@ def bench_finetune(ctx, args):
                      "flops_per_launch": round(gemm_flops / max(1, len(gemm_events))), "us_per_launch": round(gemm_ms * 1e3 / max(1, len(gemm_events)), 2),
                      "kernel": "gemm_tcgen05_kernel (all fwd/dgrad/wgrad launches of the timed steps, CUDA events per launch)", "peak_source": pk["source"] + " bf16_tflops_sustained",
                      "gemm_share_of_step": round(gemm_ms / ms_total, 4), "gemm_launches": len(gemm_events),
-                     "whole_step_frac": round(step_flops * args.steps / (ms_best / 1e3) / 1e12 / pk["bf16_tflops_sustained"], 4) if step_flops else None},
+                     "whole_step_frac": round(step_flops * args.steps / (ms_best / 1e3) / 1e12 / pk["bf16_tflops_sustained"], 4) if step_flops else None,
+                     "note": "per-launch durations from the eager run of the same steps (events cannot bracket nodes of a replayed graph); gemm_share_of_step is relative to that run"},
         "cpu_baseline": cpu, "clocks": clocks, "dp_parity": parity, "plasticity": plast, "sweep": sweep, "e2e_u8_input_pipeline": pipe, "gpu_eager": eager,
-        "ms_per_step_with_per_launch_events": round(ms_total / args.steps, 3),
+        "cuda_graph": graph_info, "ms_per_step_eager_with_per_launch_events": round(ms_total / args.steps, 3),
     }
     print(json.dumps(out))
 
@@ -639,6 +660,7 @@ def bench_sweep(ctx, args, model_name: str, images_total: int, secondary: bool =
     # ---- the only collective: ONE gather of the distance tables, outside the device-timed region, timed on its own ----
     gather_s = None
     if world > 1:
+        gather_tables(result["t"][:, :1], images_total, (images_total + world - 1) // world)  # untimed: NCCL sets the gather's channels up on first use
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()

@@ -240,21 +240,27 @@ int vb_philox_normal_f32(float* out, int64_t n_images, int64_t elems_per_image, 
 /* partials[b] = sum of x[i]^2 over block b's grid-stride share, b < n_partials (x 16-byte aligned). No atomics: the
  * total is bit-reproducible, so data-parallel replicas derive identical clip coefficients. */
 int vb_sumsq_partials_f32(const float* x, int64_t n, float* partials, int32_t n_partials, vb_stream_t stream);
-/* chunk_table: DEVICE array of n_chunks records {float* param; int64 arena_offset; int32 count; int32 pad} (24 bytes),
- * chunk starts 16-byte aligned. With norm = sqrt(sum of the partials) and coef = min(1, max_norm / (norm + 1e-6)):
+/* chunk_table: DEVICE array of n_chunks records {float* param; int64 arena_offset; int32 count; int32 pad; bf16* shadow}
+ * (32 bytes), chunk starts 16-byte aligned. With norm = sqrt(sum of the partials) and coef = min(1, max_norm / (norm + 1e-6)):
  *   g = coef * grad + weight_decay * p;  v = first_step ? g : momentum * v + g (skipped if momentum == 0);  p -= lr * v.
- * *grad_norm_out (optional) = norm, the value train.py logs as grad_norm. */
+ * shadow (optional per chunk): the same elements of the parameter's bf16 copy (the GEMM operand) are rewritten from the
+ * updated values in the same pass. *grad_norm_out (optional) = norm, the value train.py logs as grad_norm.
+ * hyper_dev (optional, DEVICE f32[4] = {lr, momentum, weight_decay, max_norm}) overrides the by-value hyper-parameters: a
+ * step captured in a CUDA graph then follows an LR schedule without re-capture. */
 int vb_sgd_momentum_clip_step(const void* chunk_table, int32_t n_chunks, const float* grad_arena, float* momentum_arena,
                               const float* sumsq_partials, int32_t n_partials, float* grad_norm_out, float max_norm, float lr,
-                              float momentum, float weight_decay, int32_t first_step, vb_stream_t stream);
+                              float momentum, float weight_decay, int32_t first_step, const float* hyper_dev,
+                              vb_stream_t stream);
 
 /* AdamW (torch.optim.AdamW, amsgrad off: src/vitef/optim.py:83-88) over the same arenas, clip coefficient as above:
  *   g = coef * grad;  p *= 1 - lr * weight_decay;  m += (1 - beta1)(g - m);  v = beta2 v + (1 - beta2) g^2;
- *   p -= (lr / bias_correction1) * m / (sqrt(v) / sqrt(bias_correction2) + eps),  bias_correction_i = 1 - beta_i^step. */
+ *   p -= (lr / bias_correction1) * m / (sqrt(v) / sqrt(bias_correction2) + eps),  bias_correction_i = 1 - beta_i^step.
+ * hyper_dev (optional, DEVICE f32[5] = {lr, weight_decay, max_norm, lr / bias_correction1, 1 / sqrt(bias_correction2)})
+ * overrides the by-value ones (CUDA-graph replay across steps). */
 int vb_adamw_clip_step(const void* chunk_table, int32_t n_chunks, const float* grad_arena, float* exp_avg_arena,
                        float* exp_avg_sq_arena, const float* sumsq_partials, int32_t n_partials, float* grad_norm_out,
                        float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
-                       float bias_correction1, float bias_correction2, vb_stream_t stream);
+                       float bias_correction1, float bias_correction2, const float* hyper_dev, vb_stream_t stream);
 
 #ifdef __cplusplus
 }

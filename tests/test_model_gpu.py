@@ -495,3 +495,75 @@ def test_checkpoint_round_trip_like_reference_checkpointer(opt_name, tmp_path):
     assert abs(float(out[0][0]) - float(out[1][0])) <= 1e-5
     for (k, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
         assert rel_l2(b, a) <= 1e-5, (k, rel_l2(b, a))
+
+
+@pytest.mark.parametrize("opt_name", ["sgd", "adamw"])
+def test_graphed_train_step_matches_eager(opt_name):
+    """GraphedTrainStep (whole step captured in a CUDA graph, hyper-parameters read from device memory) against the eager
+    train_step on the same model / batches / LR schedule: same kernels in the same order, so after 6 steps (1 eager +
+    1 capture + 4 replays, cosine schedule with warm-up, Adam's per-step bias corrections) the parameters agree to fp32
+    summation-order noise (the qkv bias gradient is reduced with atomics: not bit-reproducible run to run): rel L2 <= 1e-5."""
+    from vit_plasticity_b200.finetune import GraphedTrainStep, build_optimizer, build_scheduler, train_step
+
+    gold = load("small")
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    xs = [O.synthetic_images(4, arch, 90 + i).to(DEV) for i in range(6)]
+    ys = [O.synthetic_labels(4, arch, 95 + i).to(DEV) for i in range(6)]
+    kw = dict(lr=1e-2, momentum=0.9) if opt_name == "sgd" else dict(lr=1e-3, weight_decay=1e-2)
+
+    def make():
+        m = build("small", gold, arch, sd)
+        m.train()
+        o = build_optimizer(m, opt_name, fused=True, **kw)
+        return m, o, build_scheduler(o, "cosine", n_steps=6, warmup=2)
+
+    m1, o1, s1 = make()
+    m2, o2, s2 = make()
+    graphed = GraphedTrainStep(m2, o2, grad_clip=1.0, scheduler=s2)
+    for i in range(6):
+        l1, g1 = train_step(m1, o1, [(xs[i], ys[i])], grad_clip=1.0, scheduler=s1)
+        l2, g2 = graphed([(xs[i], ys[i])])
+        assert abs(float(l1) - float(l2)) <= 1e-5 * abs(float(l1)) and abs(float(g1) - float(g2)) <= 1e-5 * float(g1), (i, float(l1), float(l2), float(g1), float(g2))
+    assert graphed.graph is not None and graphed.launches_per_step > 20
+    assert o1._steps == o2._steps == 6
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert rel_l2(b, a) <= 1e-5, (k, rel_l2(b, a))
+    # the bf16 shadows written by the optimizer kernel are what a fresh cast of the parameters gives
+    from vit_plasticity_b200 import ops
+
+    for p in o2._shadowed:
+        assert torch.equal(ops.shadow_bf16(p), p.detach().reshape(p.shape[0], -1).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("opt_name", ["sgd", "adamw"])
+def test_fused_and_torch_optimizer_state_dicts_interchange(opt_name):
+    """A checkpoint written with torch.optim.SGD / AdamW resumes under FusedSGD / FusedAdamW and vice versa (same state keys:
+    momentum_buffer / exp_avg, exp_avg_sq, step): the step after the hand-over equals the step of the uninterrupted run."""
+    from vit_plasticity_b200.finetune import build_optimizer, train_step
+
+    gold = load("tiny")
+    arch = arch_of(gold)
+    sd = O.init_state_dict(arch, seed=gold["weights_seed"])
+    xs = [O.synthetic_images(4, arch, 70 + i).to(DEV) for i in range(3)]
+    ys = [O.synthetic_labels(4, arch, 80 + i).to(DEV) for i in range(3)]
+    kw = dict(lr=1e-2, momentum=0.9) if opt_name == "sgd" else dict(lr=1e-3, weight_decay=1e-2)
+
+    def make(fused):
+        m = build("tiny", gold, arch, sd)
+        m.train()
+        return m, build_optimizer(m, opt_name, fused=fused, **kw)
+
+    for first_fused in (True, False):
+        ma, oa = make(first_fused)  # runs steps 0, 1 then hands over
+        mref, oref = make(first_fused)  # uninterrupted: steps 0, 1, 2
+        for i in range(2):
+            train_step(ma, oa, [(xs[i], ys[i])], grad_clip=1.0)
+            train_step(mref, oref, [(xs[i], ys[i])], grad_clip=1.0)
+        mb, ob = make(not first_fused)
+        mb.load_state_dict(ma.state_dict())
+        ob.load_state_dict(oa.state_dict())
+        train_step(mb, ob, [(xs[2], ys[2])], grad_clip=1.0)
+        train_step(mref, oref, [(xs[2], ys[2])], grad_clip=1.0)
+        for (k, a), (_, b) in zip(mref.state_dict().items(), mb.state_dict().items()):
+            assert rel_l2(b, a) <= 2e-5, (first_fused, k, rel_l2(b, a))

@@ -129,11 +129,11 @@ SIGNATURES = {
     "vb_sumsq_partials_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
     "vb_sgd_momentum_clip_step": (
         c_int32,
-        [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_float, c_float, c_float, c_float, c_int32, c_void_p],
+        [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_float, c_float, c_float, c_float, c_int32, c_void_p, c_void_p],
     ),
     "vb_adamw_clip_step": (
         c_int32,
-        [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p] + [c_float] * 8 + [c_void_p],
+        [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p] + [c_float] * 8 + [c_void_p, c_void_p],
     ),
 }
 
@@ -498,17 +498,18 @@ def sumsq_partials_f32(x: torch.Tensor, partials: torch.Tensor) -> None:
     _check(lib().vb_sumsq_partials_f32(x.data_ptr(), x.numel(), partials.data_ptr(), partials.numel(), _stream()), "vb_sumsq_partials_f32")
 
 
-def adamw_clip_step(table, n_chunks, grad_arena, exp_avg, exp_avg_sq, partials, norm_out, max_norm, lr, beta1, beta2, eps, weight_decay, bc1, bc2):
+def adamw_clip_step(table, n_chunks, grad_arena, exp_avg, exp_avg_sq, partials, norm_out, max_norm, lr, beta1, beta2, eps, weight_decay, bc1, bc2, hyper=None):
     _check(
         lib().vb_adamw_clip_step(table.data_ptr(), n_chunks, grad_arena.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), partials.data_ptr(), partials.numel(),
-                                 _ptr(norm_out), float(max_norm), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), float(bc1), float(bc2), _stream()),
+                                 _ptr(norm_out), float(max_norm), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), float(bc1), float(bc2),
+                                 _ptr(hyper), _stream()),
         "vb_adamw_clip_step",
     )
 
 
-def sgd_momentum_clip_step(table, n_chunks, grad_arena, momentum_arena, partials, norm_out, max_norm, lr, momentum, weight_decay, first_step):
+def sgd_momentum_clip_step(table, n_chunks, grad_arena, momentum_arena, partials, norm_out, max_norm, lr, momentum, weight_decay, first_step, hyper=None):
     _check(
         lib().vb_sgd_momentum_clip_step(table.data_ptr(), n_chunks, grad_arena.data_ptr(), _ptr(momentum_arena), partials.data_ptr(), partials.numel(),
-                                        _ptr(norm_out), float(max_norm), float(lr), float(momentum), float(weight_decay), int(first_step), _stream()),
+                                        _ptr(norm_out), float(max_norm), float(lr), float(momentum), float(weight_decay), int(first_step), _ptr(hyper), _stream()),
         "vb_sgd_momentum_clip_step",
     )

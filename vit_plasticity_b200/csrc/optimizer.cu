@@ -55,16 +55,34 @@ struct OptChunk {
     long long arena_off; // same element inside the gradient / momentum arenas
     int count;
     int pad;
+    bf16* shadow;        // optional: same element inside the parameter's bf16 shadow copy (the GEMM operand), refreshed here
 };
+
+// bf16 shadow of four / one freshly updated parameter values: saves the stand-alone cast pass (one launch per weight matrix
+// and a second read of every parameter) that would otherwise follow the optimizer step
+__device__ __forceinline__ void store_shadow4(bf16* shadow, int i, const float4& p4) {
+    if (shadow != nullptr) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16x2(p4.x, p4.y), pack_bf16x2(p4.z, p4.w));
+}
+
+// Hyper-parameters by value or, when `hyper` is given, from device memory (so a step captured in a CUDA graph follows an LR
+// schedule / Adam's bias corrections without being re-captured).
+//   SGD:   hyper = {lr, momentum, weight_decay, max_norm}
+//   AdamW: hyper = {lr, weight_decay, max_norm, lr / bc1, 1 / sqrt(bc2)}
 
 // coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))  (torch.nn.utils.clip_grad_norm_);  g <- coef g;
 // v <- momentum v + g  (first step: v = g);  p <- p - lr (v or g)
 __global__ void __launch_bounds__(OPT_THREADS)
 sgd_momentum_clip_kernel(const OptChunk* __restrict__ table, const float* __restrict__ grad, float* __restrict__ mom,
                          const float* __restrict__ sumsq_partials, int n_partials, float* __restrict__ norm_out, float max_norm,
-                         float lr, float momentum, float weight_decay, int first_step) {
+                         float lr, float momentum, float weight_decay, int first_step, const float* __restrict__ hyper) {
     __shared__ float red[OPT_THREADS / 32];
     const OptChunk c = table[blockIdx.x];
+    if (hyper != nullptr) {
+        lr = __ldg(hyper);
+        momentum = __ldg(hyper + 1);
+        weight_decay = __ldg(hyper + 2);
+        max_norm = __ldg(hyper + 3);
+    }
     float part = 0.f;
     for (int i = threadIdx.x; i < n_partials; i += OPT_THREADS) part += __ldg(sumsq_partials + i);  // fixed order per thread
     const float norm = sqrtf(block_sum_deterministic(part, red));
@@ -99,6 +117,7 @@ sgd_momentum_clip_kernel(const OptChunk* __restrict__ table, const float* __rest
         p4.z = fmaf(-lr, g4.z, p4.z);
         p4.w = fmaf(-lr, g4.w, p4.w);
         reinterpret_cast<float4*>(p)[i] = p4;
+        store_shadow4(c.shadow, i, p4);
     }
     for (int i = (n4 << 2) + threadIdx.x; i < c.count; i += OPT_THREADS) {
         float gi = fmaf(weight_decay, p[i], g[i] * coef);
@@ -107,7 +126,9 @@ sgd_momentum_clip_kernel(const OptChunk* __restrict__ table, const float* __rest
             v[i] = vi;
             gi = vi;
         }
-        p[i] = fmaf(-lr, gi, p[i]);
+        const float pn = fmaf(-lr, gi, p[i]);
+        p[i] = pn;
+        if (c.shadow != nullptr) c.shadow[i] = __float2bfloat16_rn(pn);
     }
 }
 
@@ -118,9 +139,16 @@ __global__ void __launch_bounds__(OPT_THREADS)
 adamw_clip_kernel(const OptChunk* __restrict__ table, const float* __restrict__ grad, float* __restrict__ exp_avg,
                   float* __restrict__ exp_avg_sq, const float* __restrict__ sumsq_partials, int n_partials,
                   float* __restrict__ norm_out, float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
-                  float step_size, float inv_bc2_sqrt) {
+                  float step_size, float inv_bc2_sqrt, const float* __restrict__ hyper) {
     __shared__ float red[OPT_THREADS / 32];
     const OptChunk c = table[blockIdx.x];
+    if (hyper != nullptr) {
+        lr = __ldg(hyper);
+        weight_decay = __ldg(hyper + 1);
+        max_norm = __ldg(hyper + 2);
+        step_size = __ldg(hyper + 3);
+        inv_bc2_sqrt = __ldg(hyper + 4);
+    }
     float part = 0.f;
     for (int i = threadIdx.x; i < n_partials; i += OPT_THREADS) part += __ldg(sumsq_partials + i);
     const float norm = sqrtf(block_sum_deterministic(part, red));
@@ -149,8 +177,12 @@ adamw_clip_kernel(const OptChunk* __restrict__ table, const float* __restrict__ 
         reinterpret_cast<float4*>(m)[i] = m4;
         reinterpret_cast<float4*>(v)[i] = v4;
         reinterpret_cast<float4*>(p)[i] = p4;
+        store_shadow4(c.shadow, i, p4);
     }
-    for (int i = (n4 << 2) + threadIdx.x; i < c.count; i += OPT_THREADS) upd(g[i], m[i], v[i], p[i]);
+    for (int i = (n4 << 2) + threadIdx.x; i < c.count; i += OPT_THREADS) {
+        upd(g[i], m[i], v[i], p[i]);
+        if (c.shadow != nullptr) c.shadow[i] = __float2bfloat16_rn(p[i]);
+    }
 }
 
 }  // namespace vb
@@ -166,14 +198,15 @@ extern "C" int vb_sumsq_partials_f32(const float* x, int64_t n, float* partials,
 
 extern "C" int vb_sgd_momentum_clip_step(const void* chunk_table, int32_t n_chunks, const float* grad_arena, float* momentum_arena,
                                          const float* sumsq_partials, int32_t n_partials, float* grad_norm_out, float max_norm,
-                                         float lr, float momentum, float weight_decay, int32_t first_step, vb_stream_t stream_) {
+                                         float lr, float momentum, float weight_decay, int32_t first_step, const float* hyper_dev,
+                                         vb_stream_t stream_) {
     using namespace vb;
     VB_CHECK_ARG(chunk_table && grad_arena && sumsq_partials && n_chunks > 0 && n_partials > 0, "vb_sgd_momentum_clip_step: bad args");
     VB_CHECK_ARG(momentum == 0.f || momentum_arena != nullptr, "vb_sgd_momentum_clip_step: momentum needs a momentum arena");
-    VB_CHECK_ARG(sizeof(OptChunk) == 24, "vb_sgd_momentum_clip_step: chunk layout");
+    VB_CHECK_ARG(sizeof(OptChunk) == 32, "vb_sgd_momentum_clip_step: chunk layout");
     sgd_momentum_clip_kernel<<<n_chunks, OPT_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(
         static_cast<const OptChunk*>(chunk_table), grad_arena, momentum_arena, sumsq_partials, n_partials, grad_norm_out, max_norm, lr,
-        momentum, weight_decay, first_step);
+        momentum, weight_decay, first_step, hyper_dev);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
@@ -181,14 +214,14 @@ extern "C" int vb_sgd_momentum_clip_step(const void* chunk_table, int32_t n_chun
 extern "C" int vb_adamw_clip_step(const void* chunk_table, int32_t n_chunks, const float* grad_arena, float* exp_avg_arena,
                                   float* exp_avg_sq_arena, const float* sumsq_partials, int32_t n_partials, float* grad_norm_out,
                                   float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                  float bias_correction1, float bias_correction2, vb_stream_t stream_) {
+                                  float bias_correction1, float bias_correction2, const float* hyper_dev, vb_stream_t stream_) {
     using namespace vb;
     VB_CHECK_ARG(chunk_table && grad_arena && exp_avg_arena && exp_avg_sq_arena && sumsq_partials && n_chunks > 0 && n_partials > 0,
                  "vb_adamw_clip_step: bad args");
     VB_CHECK_ARG(bias_correction1 > 0.f && bias_correction2 > 0.f, "vb_adamw_clip_step: bias corrections must be > 0");
     adamw_clip_kernel<<<n_chunks, OPT_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(
         static_cast<const OptChunk*>(chunk_table), grad_arena, exp_avg_arena, exp_avg_sq_arena, sumsq_partials, n_partials, grad_norm_out,
-        max_norm, lr, beta1, beta2, eps, weight_decay, lr / bias_correction1, 1.f / sqrtf(bias_correction2));
+        max_norm, lr, beta1, beta2, eps, weight_decay, lr / bias_correction1, 1.f / sqrtf(bias_correction2), hyper_dev);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }

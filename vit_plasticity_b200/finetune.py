@@ -104,7 +104,9 @@ class FusedSGD(torch.optim.Optimizer):
     CHUNK = 65536
 
     def __init__(self, params, lr: float = 1e-3, momentum: float = 0.0, weight_decay: float = 0.0, grad_arena=None):
-        super().__init__(list(params), dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        # the remaining keys are torch.optim.SGD's own group defaults: a state dict of this optimizer loads into the unfused one
+        super().__init__(list(params), dict(lr=lr, momentum=momentum, weight_decay=weight_decay, dampening=0.0, nesterov=False, maximize=False,
+                                            foreach=None, differentiable=False, fused=None))
         if len(self.param_groups) != 1:
             raise ValueError("FusedSGD supports a single parameter group")
         self.trainable = [p for p in self.param_groups[0]["params"] if p.requires_grad]
@@ -127,19 +129,30 @@ class FusedSGD(torch.optim.Optimizer):
                 off += pad4(p.numel())
             self.arena = torch.zeros(off, device=dev, dtype=torch.float32)
         self.momentum_arena = torch.zeros_like(self.arena) if momentum else None
+        # bf16 shadows (the GEMM operands, ops.shadow_bf16) of the weight matrices are rewritten by the update kernel itself:
+        # no cast launch per matrix and no second read of the parameters after the step
+        from . import ops
+
+        self._shadowed = [p for p in self.trainable if p.dim() >= 2 and p.shape[0] > 1]
+        shadow_ptr = {p: ops.shadow_bf16(p).data_ptr() for p in self._shadowed}
         rows = []
         for p in self.trainable:
+            sh = shadow_ptr.get(p, 0)
             for c0 in range(0, p.numel(), self.CHUNK):
-                rows.append((p.data_ptr() + 4 * c0, self.offset[p] + c0, min(self.CHUNK, p.numel() - c0)))
-        self.table = torch.tensor(rows, dtype=torch.int64).to(dev)  # {ptr, arena offset, count | pad} = 24 bytes per chunk
+                rows.append((p.data_ptr() + 4 * c0, self.offset[p] + c0, min(self.CHUNK, p.numel() - c0), sh + 2 * c0 if sh else 0))
+        self.table = torch.tensor(rows, dtype=torch.int64).to(dev)  # {ptr, arena offset, count | pad, shadow ptr} = 32 bytes per chunk
         self.n_chunks = len(rows)
         self._ptrs = [p.data_ptr() for p in self.trainable]
         self.partials = torch.zeros(1024, device=dev, dtype=torch.float32)  # per-block sums of squares (fixed-order reduction)
         self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
+        # hyper-parameters live in device memory (the kernels read them there), so a step captured in a CUDA graph follows
+        # an LR schedule / Adam's bias corrections; re-uploaded (from pageable memory: staged at call time) only on change
+        self.hyper = torch.zeros(8, device=dev, dtype=torch.float32)
+        self._hyper_sent = None
         self._steps = 0
-        # one shared host scalar plays torch.optim.AdamW's per-parameter state["step"] (torch keeps a CPU fp32 scalar per
-        # parameter by default; every parameter of this optimizer is always at the same step)
-        self._step_tensor = torch.tensor(0.0, dtype=torch.float32)
+        # torch.optim.AdamW's per-parameter state["step"]: one CPU fp32 scalar PER parameter, as torch keeps them (a single
+        # shared tensor would be incremented once per parameter by torch's foreach step after a hand-over)
+        self._step_tensors = [torch.tensor(0.0, dtype=torch.float32) for _ in self.trainable]
         self._register_state()
         self.zero_grad()
 
@@ -154,11 +167,11 @@ class FusedSGD(torch.optim.Optimizer):
     def _register_state(self) -> None:
         """Expose the arenas through ``self.state`` as per-parameter views (what ``state_dict()`` / the reference's
         ``Checkpointer`` — ``torch.distributed.checkpoint.state_dict.get_state_dict`` — serialise)."""
-        for p in self.trainable:
+        for p, st in zip(self.trainable, self._step_tensors):
             for key, arena in self._state_arenas().items():
                 self.state[p][key] = self._arena_view(arena, p)
             if self._has_step_state():
-                self.state[p]["step"] = self._step_tensor
+                self.state[p]["step"] = st
         self.param_groups[0]["fused_steps"] = self._steps
 
     def _has_step_state(self) -> bool:
@@ -186,7 +199,7 @@ class FusedSGD(torch.optim.Optimizer):
             if steps is None and "step" in st:
                 steps = int(float(st["step"]))
         self._steps = int(steps or 0)
-        self._step_tensor = torch.tensor(float(self._steps), dtype=torch.float32)
+        self._step_tensors = [torch.tensor(float(self._steps), dtype=torch.float32) for _ in self.trainable]
         self._register_state()
 
     def _slot(self, p):
@@ -200,6 +213,32 @@ class FusedSGD(torch.optim.Optimizer):
             if g is None or g.data_ptr() != self.arena.data_ptr() + 4 * self.offset[p]:
                 p.grad = self._slot(p)
 
+    def _hyper_values(self, max_norm: float) -> list[float]:
+        group = self.param_groups[0]
+        return [group["lr"], group["momentum"], group["weight_decay"], max_norm]
+
+    def _sync_hyper(self, max_norm: float | None) -> None:
+        """Upload the hyper-parameters of the NEXT step if they changed (never inside a graph capture)."""
+        vals = self._hyper_values(float("inf") if max_norm is None else float(max_norm))
+        if vals != self._hyper_sent:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedSGD: hyper-parameters changed inside a CUDA-graph capture; call _sync_hyper before capturing")
+            self.hyper[: len(vals)].copy_(torch.tensor(vals, dtype=torch.float32))
+            self._hyper_sent = vals
+
+    def _finish_step(self) -> None:
+        """Host-side bookkeeping of one executed step (also called after every replay of a captured step)."""
+        from . import ops
+
+        self._steps += 1
+        if self._has_step_state():
+            torch._foreach_add_(self._step_tensors, 1.0)
+        self.param_groups[0]["fused_steps"] = self._steps
+        for p in self.trainable:  # the kernel wrote through raw pointers: let version-keyed caches see it
+            torch.autograd.graph.increment_version(p)
+        for p in self._shadowed:  # ... except the bf16 shadows, which the same kernel rewrote
+            ops.mark_shadow_fresh(p)
+
     @torch.no_grad()
     def step(self, closure=None, max_norm: float | None = None):
         """One update; ``max_norm`` = gradient-clipping threshold (None = no clipping). Returns the pre-clip gradient norm
@@ -207,6 +246,7 @@ class FusedSGD(torch.optim.Optimizer):
         from . import _lib as L
 
         assert closure is None
+        capturing = torch.cuda.is_current_stream_capturing()
         for p, ptr in zip(self.trainable, self._ptrs):
             if p.data_ptr() != ptr:
                 raise RuntimeError("FusedSGD: a parameter was re-allocated after the optimizer was built")
@@ -216,15 +256,13 @@ class FusedSGD(torch.optim.Optimizer):
             if g.data_ptr() != self.arena.data_ptr() + 4 * self.offset[p]:  # someone replaced .grad: fold it in
                 self._slot(p).add_(g)
                 p.grad = self._slot(p)
+        if not capturing:
+            self._sync_hyper(max_norm)
         L.sumsq_partials_f32(self.arena, self.partials)
         self._update(float("inf") if max_norm is None else max_norm)
-        self._steps += 1
-        self._step_tensor += 1.0
-        self.param_groups[0]["fused_steps"] = self._steps
-        for p in self.trainable:  # the kernel wrote through raw pointers: let version-keyed caches (bf16 shadows) see it
-            torch.autograd.graph.increment_version(p)
+        if not capturing:  # a capture executes nothing: GraphedTrainStep books every replay
+            self._finish_step()
         return self.grad_norm[0]
-
 
     def _update(self, max_norm: float) -> None:
         from . import _lib as L
@@ -233,7 +271,7 @@ class FusedSGD(torch.optim.Optimizer):
         # first_step = False always: the momentum arena starts at zero, and momentum * 0 + g == g is exactly torch's
         # first-step "buf = grad"; a special case here would overwrite momentum buffers loaded from a checkpoint
         L.sgd_momentum_clip_step(self.table, self.n_chunks, self.arena, self.momentum_arena, self.partials, self.grad_norm, max_norm,
-                                 group["lr"], group["momentum"], group["weight_decay"], False)
+                                 group["lr"], group["momentum"], group["weight_decay"], False, hyper=self.hyper)
 
 
 class FusedAdamW(FusedSGD):
@@ -243,7 +281,7 @@ class FusedAdamW(FusedSGD):
 
     def __init__(self, params, lr: float = 1e-3, weight_decay: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-8, grad_arena=None):
         super().__init__(params, lr=lr, momentum=0.0, weight_decay=weight_decay, grad_arena=grad_arena)
-        self.param_groups[0].update(betas=tuple(betas), eps=eps)
+        self.param_groups[0].update(betas=tuple(betas), eps=eps, amsgrad=False, capturable=False, decoupled_weight_decay=True)  # torch.optim.AdamW's keys
         self.exp_avg = torch.zeros_like(self.arena)
         self.exp_avg_sq = torch.zeros_like(self.arena)
         self._register_state()
@@ -256,6 +294,12 @@ class FusedAdamW(FusedSGD):
     def _has_step_state(self) -> bool:
         return hasattr(self, "exp_avg")
 
+    def _hyper_values(self, max_norm: float) -> list[float]:
+        group = self.param_groups[0]
+        b1, b2 = group["betas"]
+        t = self._steps + 1
+        return [group["lr"], group["weight_decay"], max_norm, group["lr"] / (1.0 - b1**t), 1.0 / math.sqrt(1.0 - b2**t)]
+
     def _update(self, max_norm: float) -> None:
         from . import _lib as L
 
@@ -263,7 +307,7 @@ class FusedAdamW(FusedSGD):
         b1, b2 = group["betas"]
         t = self._steps + 1
         L.adamw_clip_step(self.table, self.n_chunks, self.arena, self.exp_avg, self.exp_avg_sq, self.partials, self.grad_norm, max_norm,
-                          group["lr"], b1, b2, group["eps"], group["weight_decay"], 1.0 - b1**t, 1.0 - b2**t)
+                          group["lr"], b1, b2, group["eps"], group["weight_decay"], 1.0 - b1**t, 1.0 - b2**t, hyper=self.hyper)
 
 
 def build_optimizer(model: nn.Module, optimizer: str = "sgd", lr: float = 1e-3, momentum: float = 0.0, weight_decay: float = 0.0, fused: bool = False):
@@ -286,8 +330,11 @@ def build_optimizer(model: nn.Module, optimizer: str = "sgd", lr: float = 1e-3, 
             raise ValueError(f"Unknown optimizer '{optimizer}'. Choose between 'adamw' and 'sgd'.")
 
 
-def lr_factor(step: int, scheduler: str, n_steps: int, warmup: int = 2000, min_factor: float = 0.0) -> float:
-    """constant / linear / cosine multipliers with warm-up (optim.py:119-196; default warmup 2000, :113)."""
+def lr_factor(step: int, scheduler: str, n_steps: int, warmup: int = 2000, min_factor: float = 0.0, decay_fraction: float = 0.1,
+              cycle_length: float = 1.0) -> float:
+    """constant / linear / cosine / wsd multipliers with warm-up (optim.py:119-265; defaults of SchedulerConfig, :113-116).
+    wsd (warm-up, stable, decay; optim.py:200-265): cycles of ``n_steps * cycle_length`` steps whose last ``decay_fraction``
+    decays as 1 / (t / min_factor + 1 - t)."""
     match scheduler.lower():
         case "constant":
             return 1.0
@@ -300,12 +347,25 @@ def lr_factor(step: int, scheduler: str, n_steps: int, warmup: int = 2000, min_f
                     return min_factor + 0.5 * (1 - min_factor) * (math.cos(math.pi * s) + 1)
                 return min_factor + (1 - min_factor) * (1 - s)
             return min_factor
+        case "wsd":
+            cycle = int(n_steps * cycle_length)
+            end = cycle * (step // cycle + 1)  # last step of the current cycle
+            if step == n_steps:  # the final step closes the last cycle instead of opening a new one
+                end = n_steps
+            decay = int(end * decay_fraction)
+            if step < warmup:
+                return float(step) / warmup
+            if step <= end - decay:
+                return 1.0
+            t = (step - (end - decay)) / decay
+            return 1.0 / (t / min_factor + (1.0 - t))
         case _:
-            raise ValueError(f"Unknown scheduler '{scheduler}'.")
+            raise ValueError(f"Unknown scheduler '{scheduler}'. Choose between 'constant', 'linear', 'cosine' and 'wsd'.")
 
 
-def build_scheduler(optimizer, scheduler: str, n_steps: int, min_factor: float = 0.0, warmup: int = 2000):
-    return torch.optim.lr_scheduler.LambdaLR(optimizer, lambda s: lr_factor(s, scheduler, n_steps, warmup, min_factor))
+def build_scheduler(optimizer, scheduler: str, n_steps: int, min_factor: float = 0.0, warmup: int = 2000, decay_fraction: float = 0.1,
+                    cycle_length: float = 1.0):
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, lambda s: lr_factor(s, scheduler, n_steps, warmup, min_factor, decay_fraction, cycle_length))
 
 
 def train_step(model, optimizer, batches, grad_clip: float | None, scheduler=None, after_backward=None):
@@ -339,3 +399,74 @@ def train_step(model, optimizer, batches, grad_clip: float | None, scheduler=Non
         scheduler.step()
     optimizer.zero_grad()
     return loss.detach() * acc, grad_norm
+
+
+class GraphedTrainStep:
+    """``train_step`` for fixed-shape batches, captured ONCE in a CUDA graph and replayed: one graph launch per optimisation
+    step instead of ~300 kernel launches issued from Python (forward, loss, backward, the data-parallel bucket all-reduces,
+    clip + optimizer step and the gradient-arena reset are all inside the graph).
+
+    The first call runs the step eagerly (it also performs every one-time initialisation a capture must not contain), the
+    second call captures and replays, later calls copy the batch into the static input buffers and replay. Requires the
+    fused arena optimizers (:class:`FusedSGD` / :class:`FusedAdamW`): their hyper-parameters are read from device memory, so
+    an LR schedule (``scheduler.step()`` runs on the host after every replay) or Adam's bias corrections need no re-capture.
+    Returns (loss, pre-clip grad norm) like ``train_step``: 0-dim device tensors that the NEXT call overwrites.
+    """
+
+    def __init__(self, model, optimizer, grad_clip: float | None, scheduler=None, after_backward=None, grad_acc_steps: int = 1):
+        if not isinstance(optimizer, FusedSGD):
+            raise TypeError("GraphedTrainStep needs a fused arena optimizer (build_optimizer(..., fused=True))")
+        self.model, self.optimizer, self.grad_clip, self.scheduler, self.after_backward = model, optimizer, grad_clip, scheduler, after_backward
+        self.acc = grad_acc_steps
+        self.graph = None
+        self.static = None  # [(x, y)] static input buffers
+        self.out = None
+        self._calls = 0
+        self._sig = None
+        self.launches_per_step = None
+
+    def _signature(self, batches):
+        return tuple((tuple(x.shape), x.dtype, tuple(y.shape), y.dtype) for x, y in batches) + (self.grad_clip,)
+
+    def _capture(self, batches):
+        from . import _lib as L
+
+        dev = batches[0][0].device
+        self.static = [(torch.empty_like(x), torch.empty_like(y)) for x, y in batches]
+        for (sx, sy), (x, y) in zip(self.static, batches):
+            sx.copy_(x)
+            sy.copy_(y)
+        # every weight's bf16 shadow is rewritten by the optimizer kernel inside the graph; anything still stale now (e.g. a
+        # frozen matrix touched by load_state_dict) is cast here, outside, once
+        self.optimizer._sync_hyper(self.grad_clip)
+        torch.cuda.synchronize(dev)
+        before = L.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = train_step(self.model, self.optimizer, self.static, self.grad_clip, scheduler=None, after_backward=self.after_backward)
+        self.launches_per_step = L.launch_count() - before
+
+    def __call__(self, batches):
+        if len(batches) != self.acc:
+            raise ValueError(f"GraphedTrainStep was built for {self.acc} micro-batch(es), got {len(batches)}")
+        self._calls += 1
+        sig = self._signature(batches)
+        if self._calls == 1 or (self.graph is None and self._sig != sig):
+            self._sig = sig
+            return train_step(self.model, self.optimizer, batches, self.grad_clip, self.scheduler, self.after_backward)
+        if self._sig != sig:
+            raise ValueError("GraphedTrainStep: batch shapes / dtypes changed after the capture")
+        if self.graph is None:
+            self._capture(batches)
+        else:
+            for (sx, sy), (x, y) in zip(self.static, batches):
+                if x.data_ptr() != sx.data_ptr():
+                    sx.copy_(x, non_blocking=True)
+                if y.data_ptr() != sy.data_ptr():
+                    sy.copy_(y, non_blocking=True)
+        self.optimizer._sync_hyper(self.grad_clip)
+        self.graph.replay()
+        self.optimizer._finish_step()
+        if self.scheduler is not None:
+            self.scheduler.step()
+        return self.out

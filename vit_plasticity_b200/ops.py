@@ -58,6 +58,14 @@ def shadow_bf16(p: torch.Tensor) -> torch.Tensor:
     return w16
 
 
+def mark_shadow_fresh(p: torch.Tensor) -> None:
+    """The bf16 shadow of ``p`` was rewritten by the kernel that updated ``p`` (the fused optimizer step): record the
+    parameter's current version, so the next forward does not launch a cast."""
+    hit = _shadow.get(id(p))
+    if hit is not None and hit[0]() is p:
+        _shadow[id(p)] = (hit[0], (p.data_ptr(), p._version), hit[2])
+
+
 # --------------------------------------------------------------------------------------------------
 # in-place parameter gradients
 # --------------------------------------------------------------------------------------------------
