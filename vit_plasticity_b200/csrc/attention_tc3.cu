@@ -1127,6 +1127,12 @@ static_assert(KD_SMEM <= 232448, "shared memory budget");
 constexpr uint32_t KD_COL_DV = 256, KD_COL_DK = 320, KD_COL_DQ = 384;
 constexpr int KD_THREADS = 24 * 32;
 
+// EARLY = true (default): ONE fp32 chunk buffer [0,128) that the math warps hand back as soon as its S^T / dP^T columns are in
+// their registers, and two packed buffers [128,192) [192,256) (P^T at +0, dS^T at +32, 16 columns per 32 queries) for the A
+// operands of MMA2: the next chunk's MMA1 runs while this chunk is still being exponentiated. With EARLY = false the packed
+// values overwrite the fp32 ones in place in two chunk buffers, so MMA1 of chunk g + 2 has to wait for MMA2 of chunk g, and
+// the math warps spend a third of their time waiting for scores (ncu: 34 % of the stall samples on that one wait).
+template <bool EARLY>
 __global__ void __launch_bounds__(KD_THREADS, 1)
 attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const __grid_constant__ CUtensorMap tmKV0, const __grid_constant__ CUtensorMap tmKV1,
@@ -1143,8 +1149,8 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 512);
     uint64_t *qdo_full = bars, *qdo_empty = bars + 2, *kv_full = bars + 4, *kv_empty = bars + 6, *s_ready = bars + 8,
              *p_ready = bars + 10, *c_free = bars + 12, *ds_free = bars + 14, *kv_acc_ready = bars + 16, *kv_acc_free = bars + 17,
-             *q_acc_ready = bars + 18, *q_acc_free = bars + 19;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+             *q_acc_ready = bars + 18, *q_acc_free = bars + 19, *sd_free = bars + 20;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -1175,6 +1181,7 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             mbar_init(kv_acc_free, DRAIN_WARPS);
             mbar_init(q_acc_ready, 1);
             mbar_init(q_acc_free, DRAIN_WARPS);
+            mbar_init(sd_free, GROUP_WARPS);
             fence_barrier_init();
         }
         __syncwarp();
@@ -1301,7 +1308,10 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             if ((g & 7) == 0) mbar_wait(&qdo_full[s], (n >> 1) & 1, 73);
             if (c == 0) mbar_wait(&kv_full[j], n & 1, 78);
             if (lane == 0) KD_STAMP(g, 3);
-            mbar_wait(&c_free[cb], ((g >> 1) & 1) ^ 1, 79);
+            if (EARLY)
+                mbar_wait(sd_free, (g & 1) ^ 1, 79);  // the math group of chunk g - 1 holds its scores in registers
+            else
+                mbar_wait(&c_free[cb], ((g >> 1) & 1) ^ 1, 79);
             if (lane == 0) KD_STAMP(g, 4);
             tc_fence_after();
             if (elect_one()) {
@@ -1310,7 +1320,7 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 const uint32_t a1 = smem_lo + A_K + j * TILE16, a2 = smem_lo + A_V + j * TILE16;
                 const uint32_t b1 = qdo + crow, b2 = qdo + (OPER_BYTES >> 4) + crow;
                 const uint32_t idesc = c == 3 ? idesc16 : idesc64;
-                const uint32_t d = tmem_base + cb * 128;
+                const uint32_t d = tmem_base + (EARLY ? 0 : cb * 128);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_bf16_ss(d, make_desc((a1 | LBO_K) + 2 * k, DESC_HI), make_desc((b1 | LBO_K) + 2 * k, DESC_HI), idesc, k > 0);
@@ -1340,14 +1350,15 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 const uint32_t qdo = smem_lo + ((KD_OFF_QDO + s * KD_QDO_BYTES) >> 4);
                 const uint32_t crow = c * 64 * 8;
                 const int ksteps = c == 3 ? 1 : 4;  // 16 queries per k-step
-                const uint32_t pbuf = tmem_base + cb * 128;
+                const uint32_t pbuf = tmem_base + (EARLY ? 128 + cb * 64 : cb * 128);
                 const uint32_t domn = (qdo + (OPER_BYTES >> 4) + crow) | LBO_MN, qmn = (qdo + crow) | LBO_MN;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (k < ksteps) {
-                        const uint32_t acol = (k >> 1) * 32 + (k & 1) * 8;
-                        umma_bf16_ts(tmem_base + KD_COL_DV, pbuf + acol, make_desc(domn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));       // dV_j += P^T dO_c
-                        umma_bf16_ts(tmem_base + KD_COL_DK, pbuf + 64 + acol, make_desc(qmn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));  // dK_j += dS^T Q_c
+                        const uint32_t acol = EARLY ? k * 8 : (k >> 1) * 32 + (k & 1) * 8;
+                        const uint32_t dscol = (EARLY ? 32 : 64) + acol;
+                        umma_bf16_ts(tmem_base + KD_COL_DV, pbuf + acol, make_desc(domn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));    // dV_j += P^T dO_c
+                        umma_bf16_ts(tmem_base + KD_COL_DK, pbuf + dscol, make_desc(qmn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));  // dK_j += dS^T Q_c
                     }
                 umma_commit(&c_free[cb]);
                 if (c & 1) {
@@ -1395,10 +1406,26 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             if (stp) KD_STAMP(g, 5);
             mbar_wait(&ds_free[cc >> 1], ((2 * n + j) & 1) ^ 1, 81);
             if (stp) KD_STAMP(g, 6);
+            // one barrier per math group in both modes (EARLY shares the fp32 buffer, not the barrier: a parity-1 wait on a
+            // barrier shared by both groups would pass at once for group 1's first chunk)
             mbar_wait(&s_ready[cb], (g >> 1) & 1, 75);
             if (stp) KD_STAMP(g, 7);
             tc_fence_after();
-            const uint32_t sbuf = lane_addr + cb * 128, dbuf = sbuf + 64;
+            const uint32_t sbuf = lane_addr + (EARLY ? 0 : cb * 128), dbuf = sbuf + 64;
+            // where the packed A operands of MMA2 go: over the fp32 values, or (EARLY) into this chunk's packed buffer
+            const uint32_t pk_p = EARLY ? lane_addr + 128 + cb * 64 + hf * 16 : sbuf + c0;
+            const uint32_t pk_ds = EARLY ? pk_p + 32 : dbuf + c0;
+            auto release_scores = [&]() {
+                if (EARLY) {
+                    // the fp32 scores of this chunk are in registers (or not needed by this warp): MMA1 may refill the buffer;
+                    // the packed buffer is free once the MMA2 that read it two chunks ago has completed
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sd_free);
+                    mbar_wait(&c_free[cb], ((g >> 1) & 1) ^ 1, 82);
+                    tc_fence_after();
+                }
+            };
             const uint32_t ds_chunk = ds_row + (cc >> 1) * KD_DS_BLOCK + (cc & 1) * 16384;
             if (cc < 3) {
                 uint32_t sv[32], dv[32];
@@ -1407,6 +1434,7 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 tmem_ld_wait();
                 reg_fence(sv);
                 reg_fence(dv);
+                release_scores();
                 if (stp) KD_STAMP(g, 10);
                 uint32_t pp[16], pd[16];
                 const float* lq = sLs + cc * 64 + c0;  // same address for the whole warp: smem broadcast
@@ -1427,8 +1455,8 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                     pd[2 * gq + 1] = pack_bf16x2(ds[2], ds[3]);
                 }
                 if (stp) KD_STAMP(g, 11);
-                tmem_st_x16(sbuf + c0, pp);
-                tmem_st_x16(dbuf + c0, pd);
+                tmem_st_x16(pk_p, pp);
+                tmem_st_x16(pk_ds, pd);
                 // dS^T also as the A operand of the dQ MMA: 32 queries = 64 bytes = pieces 4 hf .. 4 hf + 3 of this key's row
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -1443,6 +1471,7 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 tmem_ld_wait();
                 reg_fence(sv);
                 reg_fence(dv);
+                release_scores();
                 uint32_t pp[8], pd[8];
                 const float* lq = sLs + 192;
                 const float* dq = sDs + 192;
@@ -1461,13 +1490,15 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                     pd[2 * gq] = pack_bf16x2(ds[0], ds[1]);
                     pd[2 * gq + 1] = pack_bf16x2(ds[2], ds[3]);
                 }
-                tmem_st_x8(sbuf, pp);
-                tmem_st_x8(dbuf, pd);
+                tmem_st_x8(pk_p, pp);
+                tmem_st_x8(pk_ds, pd);
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_chunk + ((i ^ sw) << 4)), "r"(pd[4 * i]),
                                  "r"(pd[4 * i + 1]), "r"(pd[4 * i + 2]), "r"(pd[4 * i + 3])
                                  : "memory");
+            } else {
+                release_scores();  // the upper-half warps have nothing to do in the 16-query tail chunk
             }
             if (stp) KD_STAMP(g, 8);
             tmem_st_wait();
@@ -1618,14 +1649,18 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
     rc = make_tensor_map_3d(&tmKV1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, 3 * E, L, batch, 3 * E * 2, (uint64_t)L * 3 * E * 2, 64, ROWS - 128, 1,
                             CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    static bool done_kd = false;
-    rc = set_smem(attention_bwd_kd_kernel, KD_SMEM, done_kd);
+    static bool done_kd = false, done_kd0 = false;
+    static const bool early = []() {
+        const char* e = getenv("VITB200_ATTN_BWD_EARLY");  // 0: packed operands in place, MMA1 two chunks behind MMA2 (A/B runs)
+        return !(e != nullptr && e[0] == '0');
+    }();
+    rc = early ? set_smem(attention_bwd_kd_kernel<true>, KD_SMEM, done_kd) : set_smem(attention_bwd_kd_kernel<false>, KD_SMEM, done_kd0);
     if (rc) return rc;
     if (dbg_on) {
         long long* dbg = nullptr;
         VB_CHECK_CUDA(cudaMallocManaged(&dbg, 64 * 16 * sizeof(long long)));
         VB_CHECK_CUDA(cudaMemset(dbg, 0, 64 * 16 * sizeof(long long)));
-        attention_bwd_kd_kernel<<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, dbg);
+        attention_bwd_kd_kernel<true><<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, dbg);
         VB_CHECK_CUDA(cudaStreamSynchronize(stream));
         const long long t0 = dbg[0];
         printf("[kd timing] g: mma2{waitP< waitP> accfree>} mma1{cfree< cfree>} math{start dsfree> Sready> stores> arrive> ld> math>}\n");
@@ -1637,7 +1672,10 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
         cudaFree(dbg);
         return VB_OK;
     }
-    attention_bwd_kd_kernel<<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
+    if (early)
+        attention_bwd_kd_kernel<true><<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
+    else
+        attention_bwd_kd_kernel<false><<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }
