@@ -205,3 +205,48 @@ def test_sweep_gather_reassembles_shards_in_order(tmp_path, world, n_total):
     assert table.shape == (2, 4, n_total)
     for e in range(2):
         assert (table[e] == np.arange(n_total, dtype=np.float32) + 100.0 * e).all()
+
+
+class _FakeProbeModel(nn.Module):
+    """Stands in for the Transformer on the CPU: get_pooled_probes returns rows that identify their sample."""
+
+    def __init__(self):
+        super().__init__()
+        self.p = nn.Parameter(torch.zeros(1))
+        self.blocks = [0]
+
+    def get_pooled_probes(self, x, cls_pooling=True, normalize=True):
+        v = x.reshape(x.shape[0], -1)[:, :3].float()
+        return {"block0_a": v.clone(), "block0_b": torch.cat([v, v], 1)}
+
+
+def _probe_worker(rank, world, port, outdir):
+    import numpy as np
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vit_plasticity_b200.probing import get_embeddings
+
+    loader = [(torch.arange(i * 100, i * 100 + n * 4, dtype=torch.float32).reshape(n, 4), torch.arange(n) + 10 * i) for i, n in enumerate([5, 3, 1])]
+    emb, lab = get_embeddings(_FakeProbeModel(), loader, True, device="cpu")
+    if rank == 0:
+        np.savez(os.path.join(outdir, "probe.npz"), a=emb["block0_a"], b=emb["block0_b"], lab=lab)
+    else:
+        assert emb is None and lab is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_probe_features_sharded_and_gathered_in_loader_order(tmp_path, world):
+    """Linear-probing features: every rank pools its shard of every batch, rank 0 gets the rows of all
+    taps and the labels back in the loader's sample order (ragged batches, a batch smaller than the world size)."""
+    import numpy as np
+
+    port = _free_port()
+    mp.spawn(_probe_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "probe.npz")
+    loader = [(torch.arange(i * 100, i * 100 + n * 4, dtype=torch.float32).reshape(n, 4), torch.arange(n) + 10 * i) for i, n in enumerate([5, 3, 1])]
+    ref = torch.cat([x for x, _ in loader])[:, :3].numpy()
+    assert np.array_equal(got["a"], ref)
+    assert np.array_equal(got["b"], np.concatenate([ref, ref], 1))
+    assert np.array_equal(got["lab"], torch.cat([y for _, y in loader]).numpy())

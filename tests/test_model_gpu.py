@@ -403,6 +403,18 @@ def test_decomposition_and_probes_api_tiny():
             assert v.device.type == "cpu" and v.shape == ref_rows.shape
             assert rel_l2(v, ref_rows) <= 3e-2, (k, field)
             assert torch.allclose(v.norm(dim=-1), torch.ones(v.shape[0]), atol=1e-4)
+    # the linear-probing driver (apps/vit/linear_probing.py:58-116 get_embeddings): two batches, loader order kept
+    from vit_plasticity_b200.probing import get_embeddings
+
+    h = gold["batch"] // 2
+    labels = torch.arange(gold["batch"])
+    emb, lab = get_embeddings(model, [(x[:h], labels[:h]), (x[h:], labels[h:])], cls_pooling=True)
+    assert np.array_equal(lab, labels.numpy()) and list(emb) == list(gold["probes"])
+    for k, v in emb.items():
+        ref_rows = gold["probes"][k]["cls"].float()
+        ref_rows = (ref_rows / ref_rows.norm(dim=-1, keepdim=True)).numpy()
+        assert v.dtype == np.float32 and v.shape == ref_rows.shape
+        assert rel_l2(v, ref_rows) <= 3e-2, k
     dec = model.get_decomposition(x.to(DEV))
     ref = O.decomposition(sd, x, arch)
     assert list(dec) == list(ref) and len(dec) == 1 + 5 * arch.n_layers
