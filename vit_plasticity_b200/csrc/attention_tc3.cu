@@ -25,6 +25,8 @@
 //   TMEM, so these N = 64 tiles run the tensor pipe at < 50 % of its rate: head_dim 64 bounds this kernel, not HBM.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "host_utils.h"
 #define VB_MBAR_TRAP_PRINTF 0  // no CALL in these kernels: per-role register budgets (setmaxnreg), see ptx.cuh
 #include "ptx.cuh"
@@ -426,37 +428,75 @@ __device__ __forceinline__ float expm1_neg(float w) {
     return w > -0.125f ? poly : big;
 }
 
-// One row's share of a unit: NC (64 or 48) columns starting at cbeg. Leaves packed bf16 P_a at buffer-A columns
-// [cbeg / 2, +NC / 2) and packed H at [104 + cbeg / 2, +NC / 2).
-template <int NC>
-__device__ __forceinline__ void delta_softmax_part(uint32_t lane_addr, int cbeg, int nvalid, float* sMaxA, float* sMaxW, float* sSumA,
-                                                   float* sSumG, float* sSumB, int part, int row, int quarter) {
-    const float c = 0.125f * LOG2E;
-    uint32_t v0[32], v1[NC - 32];
-    tmem_ld_32x32b_x32(lane_addr + D_COL_A + cbeg, v0);
-    if constexpr (NC == 64)
-        tmem_ld_32x32b_x32(lane_addr + D_COL_A + cbeg + 32, v1);
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+template <int W>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[W]) {
+    if constexpr (W == 16)
+        tmem_ld_32x32b_x16(taddr, r);
     else
-        tmem_ld_32x32b_x16(lane_addr + D_COL_A + cbeg + 32, v1);
+        tmem_ld_32x32b_x8(taddr, r);
+}
+template <int W>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)[W]) {
+    if constexpr (W == 16)
+        tmem_st_x16(taddr, r);
+    else if constexpr (W == 8)
+        tmem_st_x8(taddr, r);
+    else
+        tmem_st_x4(taddr, r);
+}
+
+// One row's share of a unit. The 208 score columns are 13 pieces of 16; piece q belongs to column part q & 3, and part 0
+// also owns the tail piece 12 (columns 192..207, of which L - 192 hold keys: 5 for 197 tokens), processed 8 columns at a
+// time and only as far as keys exist: every part has 48 columns of work, part 0 eight more (the contiguous 64/48/48/48 split
+// made the other twelve warps wait for part 0). Leaves packed bf16 P_a at buffer-A columns [8 q, 8 q + 8) and packed H at
+// [104 + 8 q, ...) for each of its pieces.
+template <bool TAIL>
+__device__ __forceinline__ void delta_softmax_part(uint32_t lane_addr, int L, float* sMaxA, float* sMaxW, float* sSumA, float* sSumG,
+                                                   float* sSumB, int part, int row, int quarter) {
+    const float c = 0.125f * LOG2E;
+    const int nvt = TAIL ? L - 192 : 0;  // keys in the tail piece
+    uint32_t v[3][16], vt[TAIL ? 16 : 1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tmem_ld_32x32b_x16(lane_addr + D_COL_A + 16 * (part + 4 * k), v[k]);
+    if constexpr (TAIL) tmem_ld_32x32b_x16(lane_addr + D_COL_A + 192, vt);
     tmem_ld_wait();
-    reg_fence(v0);
-    reg_fence(v1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) reg_fence(v[k]);
+    if constexpr (TAIL) reg_fence(vt);
     float m = -INFINITY, mw = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-        if (i < nvalid) m = fmaxf(m, __uint_as_float(v0[i]));
+    for (int k = 0; k < 3; ++k) {
+        const int nv = L - 16 * (part + 4 * k);
 #pragma unroll
-    for (int i = 0; i < NC - 32; ++i)
-        if (32 + i < nvalid) m = fmaxf(m, __uint_as_float(v1[i]));
+        for (int i = 0; i < 16; ++i)
+            if (i < nv) m = fmaxf(m, __uint_as_float(v[k][i]));
+    }
+    if constexpr (TAIL) {
 #pragma unroll
-    for (int pc = 0; pc < NC / 16; ++pc) {
-        uint32_t w[16];
-        tmem_ld_32x32b_x16(lane_addr + D_COL_B + cbeg + pc * 16, w);
+        for (int i = 0; i < 16; ++i)
+            if (i < nvt) m = fmaxf(m, __uint_as_float(vt[i]));
+    }
+    auto max_piece = [&](auto wtag, int col, int nv) {  // running max of the valid dS columns [col, col + W)
+        constexpr int W = decltype(wtag)::value;
+        uint32_t w[W];
+        tmem_ld_cols<W>(lane_addr + D_COL_B + col, w);
         tmem_ld_wait();
         reg_fence(w);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (pc * 16 + i < nvalid) mw = fmaxf(mw, __uint_as_float(w[i]));
+        for (int i = 0; i < W; ++i)
+            if (i < nv) mw = fmaxf(mw, __uint_as_float(w[i]));
+    };
+    using W16 = std::integral_constant<int, 16>;
+    using W8 = std::integral_constant<int, 8>;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) max_piece(W16{}, 16 * (part + 4 * k), L - 16 * (part + 4 * k));
+    if constexpr (TAIL) {
+        if (nvt > 0) max_piece(W8{}, 192, nvt);
+        if (nvt > 8) max_piece(W8{}, 200, nvt - 8);
     }
     sMaxA[part * 128 + row] = m;
     sMaxW[part * 128 + row] = mw;
@@ -467,40 +507,60 @@ __device__ __forceinline__ void delta_softmax_part(uint32_t lane_addr, int cbeg,
     // ---- p = exp2((S - m) c), kept in fp32 in the registers that held S ----
     float la = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const float a = (i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v0[i]), c, -mc)) : 0.f;
-        v0[i] = __float_as_uint(a);
-        la += a;
-    }
+    for (int k = 0; k < 3; ++k) {
+        const int nv = L - 16 * (part + 4 * k);
 #pragma unroll
-    for (int i = 0; i < NC - 32; ++i) {
-        const float a = (32 + i < nvalid) ? fast_ex2(fmaf(__uint_as_float(v1[i]), c, -mc)) : 0.f;
-        v1[i] = __float_as_uint(a);
-        la += a;
+        for (int i = 0; i < 16; ++i) {
+            const float a = (i < nv) ? fast_ex2(fmaf(__uint_as_float(v[k][i]), c, -mc)) : 0.f;
+            v[k][i] = __float_as_uint(a);
+            la += a;
+        }
+    }
+    if constexpr (TAIL) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float a = (i < nvt) ? fast_ex2(fmaf(__uint_as_float(vt[i]), c, -mc)) : 0.f;
+            vt[i] = __float_as_uint(a);
+            la += a;
+        }
     }
     // ---- g = p * expm1((dS - mw) / 8), parked in fp32 over the dS columns it came from (this thread's own columns) ----
     const float mw8 = mw * 0.125f;
     float dl = 0.f, lb = 0.f;
-    auto make_g = [&](auto& pv, int base, int col) {  // pv[base .. base + 16) hold p of columns [col, col + 16) of this part
-        uint32_t w[16];
-        tmem_ld_32x32b_x16(lane_addr + D_COL_B + cbeg + col, w);
+    auto make_g = [&](auto wtag, auto& pv, int base, int col) {  // pv[base .. base + W) hold p of columns [col, col + W)
+        constexpr int W = decltype(wtag)::value;
+        uint32_t w[W];
+        tmem_ld_cols<W>(lane_addr + D_COL_B + col, w);
         tmem_ld_wait();
         reg_fence(w);
+        float wmin = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float p0 = __uint_as_float(pv[base + i]);
+        for (int i = 0; i < W; ++i) {
             // the clamp keeps masked columns (p = 0, dS = 0 there) at expm1(0) = 0 instead of 0 * inf
-            const float g0 = p0 * expm1_neg(fminf(fmaf(__uint_as_float(w[i]), 0.125f, -mw8), 0.f));
+            const float x = fminf(fmaf(__uint_as_float(w[i]), 0.125f, -mw8), 0.f);
+            w[i] = __float_as_uint(x);
+            wmin = fminf(wmin, x);
+        }
+        // small perturbations (the usual case of a sweep): the whole warp is in the polynomial range, no exp2 at all
+        const bool poly_only = __all_sync(0xffffffffu, wmin > -0.125f);
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            const float x = __uint_as_float(w[i]), p0 = __uint_as_float(pv[base + i]);
+            const float poly = x * fmaf(x, fmaf(x, fmaf(x, 1.f / 24.f, 1.f / 6.f), 0.5f), 1.f);
+            const float e = poly_only ? poly : (x > -0.125f ? poly : fast_ex2(x * LOG2E) - 1.f);
+            const float g0 = p0 * e;
             w[i] = __float_as_uint(g0);
             dl += g0;
             lb += p0 + g0;
         }
-        tmem_st_x16(lane_addr + D_COL_B + cbeg + col, w);
+        tmem_st_cols<W>(lane_addr + D_COL_B + col, w);
     };
-    make_g(v0, 0, 0);
-    make_g(v0, 16, 16);
-    make_g(v1, 0, 32);
-    if constexpr (NC == 64) make_g(v1, 16, 48);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) make_g(W16{}, v[k], 0, 16 * (part + 4 * k));
+    if constexpr (TAIL) {
+        if (nvt > 0) make_g(W8{}, vt, 0, 192);
+        if (nvt > 8) make_g(W8{}, vt, 8, 200);
+    }
     sSumA[part * 128 + row] = la;
     sSumG[part * 128 + row] = dl;
     sSumB[part * 128 + row] = lb;
@@ -513,24 +573,39 @@ __device__ __forceinline__ void delta_softmax_part(uint32_t lane_addr, int cbeg,
     const float rho = dl * inv_la;
     // ---- P_a = p / la and H = (g - rho p) / lb, packed to bf16 over buffer A (every S column of this quarter is in
     //      registers since the first barrier) ----
-    auto pack_h = [&](auto& pv, int base, int col) {
-        uint32_t w[16], pa[8], ph[8];
-        tmem_ld_32x32b_x16(lane_addr + D_COL_B + cbeg + col, w);
+    auto pack_h = [&](auto wtag, auto& pv, int base, int col) {
+        constexpr int W = decltype(wtag)::value;
+        uint32_t w[W], pa[W / 2], ph[W / 2];
+        tmem_ld_cols<W>(lane_addr + D_COL_B + col, w);
         tmem_ld_wait();
         reg_fence(w);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < W / 2; ++i) {
             const float p0 = __uint_as_float(pv[base + 2 * i]), p1 = __uint_as_float(pv[base + 2 * i + 1]);
             pa[i] = pack_bf16x2(p0 * inv_la, p1 * inv_la);
             ph[i] = pack_bf16x2(fmaf(-rho, p0, __uint_as_float(w[2 * i])) * inv_lb, fmaf(-rho, p1, __uint_as_float(w[2 * i + 1])) * inv_lb);
         }
-        tmem_st_x8(lane_addr + D_COL_A + ((cbeg + col) >> 1), pa);
-        tmem_st_x8(lane_addr + D_COL_H + ((cbeg + col) >> 1), ph);
+        tmem_st_cols<W / 2>(lane_addr + D_COL_A + (col >> 1), pa);
+        tmem_st_cols<W / 2>(lane_addr + D_COL_H + (col >> 1), ph);
     };
-    pack_h(v0, 0, 0);
-    pack_h(v0, 16, 16);
-    pack_h(v1, 0, 32);
-    if constexpr (NC == 64) pack_h(v1, 16, 48);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pack_h(W16{}, v[k], 0, 16 * (part + 4 * k));
+    if constexpr (TAIL) {
+        // halves of the tail piece without keys: zero operands (the fp32 scores left there must not reach the MMA as bf16)
+        const uint32_t zero[4] = {0u, 0u, 0u, 0u};
+        if (nvt > 0) {
+            pack_h(W8{}, vt, 0, 192);
+        } else {
+            tmem_st_x4(lane_addr + D_COL_A + 96, zero);
+            tmem_st_x4(lane_addr + D_COL_H + 96, zero);
+        }
+        if (nvt > 8) {
+            pack_h(W8{}, vt, 8, 200);
+        } else {
+            tmem_st_x4(lane_addr + D_COL_A + 100, zero);
+            tmem_st_x4(lane_addr + D_COL_H + 100, zero);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -662,7 +737,6 @@ attention_perturb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int quarter = warp & 3, part = warp >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        const int cbeg = part == 0 ? 0 : 16 + 48 * part;  // 0, 64, 112, 160
         for (int u = 0; u < U; ++u) {
             const int t = u & 1;
             const int it = blockIdx.x + (u >> 1) * gridDim.x;
@@ -670,9 +744,9 @@ attention_perturb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             mbar_wait(s_ready, u & 1, 86);
             tc_fence_after();
             if (part == 0)
-                delta_softmax_part<64>(lane_addr, cbeg, L - cbeg, sMaxA, sMaxW, sSumA, sSumG, sSumB, part, row, quarter);
+                delta_softmax_part<true>(lane_addr, L, sMaxA, sMaxW, sSumA, sSumG, sSumB, part, row, quarter);
             else
-                delta_softmax_part<48>(lane_addr, cbeg, L - cbeg, sMaxA, sMaxW, sSumA, sSumG, sSumB, part, row, quarter);
+                delta_softmax_part<false>(lane_addr, L, sMaxA, sMaxW, sSumA, sSumG, sSumB, part, row, quarter);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
