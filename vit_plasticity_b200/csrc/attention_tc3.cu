@@ -1276,68 +1276,51 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        // Accumulators are read 32 columns at a time and packed to bf16 in registers at once, so that BOTH accumulators of a
-        // key tile (both query blocks of dQ) are out of TMEM — and handed back to the MMA issuer — before the first global
-        // store or column sum: the first MMA2 of the next tile used to wait 1 400 - 2 300 cycles for this warpgroup.
-        auto load_packed = [&](uint32_t col, uint32_t (&dst)[32]) {  // 64 fp32 columns -> 32 packed bf16x2
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t a[32];
-                tmem_ld_32x32b_x32(lane_addr + col + 32 * h, a);
-                tmem_ld_wait();
-                reg_fence(a);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) dst[16 * h + i] = pack_bf16x2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1]));
-            }
+        uint32_t a[32], a2[32];
+        auto load64 = [&](uint32_t col) {
+            tmem_ld_32x32b_x32(lane_addr + col, a);
+            tmem_ld_32x32b_x32(lane_addr + col + 32, a2);
+            tmem_ld_wait();
+            reg_fence(a);
+            reg_fence(a2);
         };
         auto release = [&](uint64_t* bar) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar);
         };
-        auto put = [&](const uint32_t (&pk)[32], bool ok, bf16* dst, float* dcol) {
+        auto put = [&](bool ok, bf16* dst, float* dcol) {
             if (ok) {
-                uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                store_32cols_bf16(dst, a, 1.f);
+                store_32cols_bf16(dst + 32, a2, 1.f);
             }
-            if (dbias != nullptr) {  // column sums of the values as stored (bf16): the qkv bias gradient
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t f[32];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float2 v2 = unpack_bf16x2(pk[16 * h + i]);
-                        f[2 * i] = __float_as_uint(v2.x);
-                        f[2 * i + 1] = __float_as_uint(v2.y);
-                    }
-                    warp_colsum32_atomic(f, ok, dcol + 32 * h, lane);
-                }
+            if (dbias != nullptr) {
+                warp_colsum32_atomic(a, ok, dcol, lane);
+                warp_colsum32_atomic(a2, ok, dcol + 32, lane);
             }
         };
         for (int n = 0; n < n_local; ++n) {
             const int it = blockIdx.x + n * gridDim.x;
             const int b = it / H, hd = it - b * H;
             bf16* dbase = dqkv + (int64_t)b * L * ld3 + hd * HD;
-            uint32_t p0[32], p1[32];
             for (int j = 0; j < 2; ++j) {
                 const int t = 2 * n + j;
                 mbar_wait(kv_acc_ready, t & 1, 74);
                 tc_fence_after();
                 const int r = j * 128 + row;  // key
-                load_packed(KD_COL_DV, p0);
-                load_packed(KD_COL_DK, p1);
+                load64(KD_COL_DV);
+                put(r < L, dbase + (int64_t)r * ld3 + 2 * E, dbias + 2 * E + hd * HD);
+                load64(KD_COL_DK);
                 release(kv_acc_free);
-                put(p0, r < L, dbase + (int64_t)r * ld3 + 2 * E, dbias + 2 * E + hd * HD);
-                put(p1, r < L, dbase + (int64_t)r * ld3 + E, dbias + E + hd * HD);
+                put(r < L, dbase + (int64_t)r * ld3 + E, dbias + E + hd * HD);
             }
             mbar_wait(q_acc_ready, n & 1, 77);
             tc_fence_after();
-            load_packed(KD_COL_DQ, p0);
-            load_packed(KD_COL_DQ + 64, p1);
+            load64(KD_COL_DQ);
+            put(row < L, dbase + (int64_t)row * ld3, dbias + hd * HD);  // queries 0..127
+            load64(KD_COL_DQ + 64);
             release(q_acc_free);
-            put(p0, row < L, dbase + (int64_t)row * ld3, dbias + hd * HD);                      // queries 0..127
-            put(p1, 128 + row < L, dbase + (int64_t)(128 + row) * ld3, dbias + hd * HD);        // queries 128..255
+            put(128 + row < L, dbase + (int64_t)(128 + row) * ld3, dbias + hd * HD);  // queries 128..255
         }
     } else if (warp >= B_WARP_TMA) {
     setmaxnreg_dec<32>();
