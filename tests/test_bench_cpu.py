@@ -1,0 +1,56 @@
+"""bench.py on the CPU: the reference arm's JSON line (driven through the UNMODIFIED reference under baseline/_ref when it is
+installed; `unavailable` otherwise) carries the keys of the benchmark contract and the same `config` the B200 arm prints,
+and the FLOP accounting of the estimator is self-consistent."""
+
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+
+
+def test_sweep_flop_accounting():
+    g1, g5 = bench.sweep_gflop("large", 1), bench.sweep_gflop("large", 5)
+    # one magnitude: the shared work is not amortised; five magnitudes: a fifth of it per pair
+    assert g1["executed_per_pair"] > g5["executed_per_pair"] > 0
+    assert abs(g5["executed_per_image"] - 5 * g5["executed_per_pair"]) < 1e-6
+    # reference-faithful 70.25 GFLOP/pair (ViT-B), 246.2 (ViT-L)
+    assert abs(bench.sweep_gflop("base", 1)["reference_faithful_per_pair"] - 70.25) < 0.05
+    assert abs(g1["reference_faithful_per_pair"] - 246.2) < 0.1
+    assert bench.sweep_gflop("base", 1)["executed_per_pair"] < 0.6 * 70.25
+
+
+def test_strong_scaling_split_and_config():
+    class A:
+        scaling, batch, global_batch = "strong", 512, 512
+
+    assert bench.per_rank_batch(A, 1) == 512 and bench.per_rank_batch(A, 8) == 64
+    A.scaling = "weak"
+    assert bench.per_rank_batch(A, 8) == 512
+    c1 = bench.finetune_config("base", 64, 8, [], 85806346, "strong")
+    assert c1["global_batch"] == 512 and c1["parallelism"] == "dp8" and c1["scaling"] == "strong"
+    with pytest.raises(SystemExit):
+        A.scaling, A.global_batch = "strong", 510
+        bench.per_rank_batch(A, 8)
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference"
+    if "unavailable" in line:  # baseline/_ref not installed on this machine
+        assert isinstance(line["unavailable"], str) and line["unavailable"]
+        return
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["unit"] == "img/s" and line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 1
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the same `config` object the B200 arm prints for this workload
+    assert line["config"] == bench.finetune_config("base", 512, 1, [], 85806346, "strong")

@@ -12,17 +12,10 @@
 // forward, per item two units (query tiles of 128 rows): S = Q_t K^T (N = 208) -> exact softmax, one TMEM read, the row
 //   split over 4 warps (64+48+48+48 columns held in registers) -> O = P V.
 //   TMEM: S/P buffers [0,208) and [208,416) (unit parity), O accumulator [416,480).
-// backward: attention_bwd_kd_kernel (key-domain schedule, the default; described at its definition below). The earlier
-// two-domain kernel (attention_bwd_persistent_kernel, kept behind VITB200_ATTN_BWD=old for bisection) works as follows:
-//   per item four units: dQ_t (t = 0,1; queries on the TMEM lanes) and dK_j/dV_j (j = 0,1; keys on the lanes,
-//   "transposed domain", so lse / delta are per-COLUMN scalars there). Each unit walks 4 column chunks (64,64,64,16):
-//   MMA1: S_c, dP_c -> math: P = exp2(S c - lse), dS = P (dP - delta) / 8 -> MMA2: accumulate.
-//   TMEM: three chunk buffers [0,128) [128,256) [256,384) (S at +0, dP at +64), accumulator [384,512). Two issuer warps:
-//   warp 17 issues every MMA1 (three chunks ahead of the math), warp 18 every MMA2; a buffer returns to MMA1 when the
-//   MMA2 that read it has completed. The two math groups (8 warps each) take alternate chunks; a separate drain warpgroup
-//   reads the accumulators out. No masking is needed: padded K/V/Q/dO rows are zero and padded lse entries are +inf (p = 0).
+// backward: attention_bwd_kd_kernel (key-domain schedule, described at its definition below). The two-domain kernel of round 1
+//   (S / dP computed in the query AND the key domain, 690 -> 525 us) was removed in round 2; git history has it (80de1b7).
 //   Measured (tools/microbench/mma_rate.cu): a 128xNx16 MMA costs ~44 + N/2 cycles with A in smem, ~12 + N/2 with A in
-//   TMEM, so these N = 64 tiles run the tensor pipe at < 50 % of its rate: head_dim 64 bounds this kernel, not HBM.
+//   TMEM, so N = 64 tiles run the tensor pipe at < 50 % of its rate: head_dim 64 bounds these kernels, not HBM.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -814,367 +807,10 @@ __global__ void attention_delta_kernel(const bf16* __restrict__ out, const bf16*
     }
 }
 
-constexpr int B_STAGE = 4 * OPER_BYTES;  // Q, K, V, dO
-constexpr int B_TAIL = 6144;             // lse / delta staging + barriers; also absorbs the 48-row over-read of the last tile
-constexpr int B_SMEM = 2 * B_STAGE + B_TAIL + 1024;
-constexpr uint32_t OFF_Q = 0, OFF_K = OPER_BYTES >> 4, OFF_V = (2 * OPER_BYTES) >> 4, OFF_DO = (3 * OPER_BYTES) >> 4;  // 16-B units
-constexpr uint32_t B_COL_ACC = 384;
 constexpr int GROUP_WARPS = 8;
 constexpr int B_WARP_TMA = 16, B_WARP_MMA1 = 17, B_WARP_MMA2 = 18;  // (warp 19 idles: roles are assigned per warpgroup)
 constexpr int B_WARP_DRAIN0 = 20, DRAIN_WARPS = 4;                   // one warp per TMEM lane quarter
 constexpr int B_THREADS = 24 * 32;
-
-__global__ void __launch_bounds__(B_THREADS, 1)
-attention_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                                const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
-                                float* __restrict__ dbias, int L, int H, int n_items, long long* __restrict__ dbg) {
-    // dbias (optional, f32 [3E], caller-zeroed): += column sums of dqkv = the qkv Linear's bias gradient, reduced from the
-    // accumulators as they are drained: +44 us on this kernel against a 100 us column-sum pass over dqkv per layer
-    // dbg (development only, normally nullptr): clock64 stamps of chunks [32, 96) of CTA 0, 16 slots per chunk
-#define VB_STAMP(g, slot)                                                                                   \
-    do {                                                                                                    \
-        if (dbg != nullptr && blockIdx.x == 0 && (g) >= 32 && (g) < 96) dbg[((g)-32) * 16 + (slot)] = clock64(); \
-    } while (0)
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = align_smem(smem_raw);
-    float* sL = reinterpret_cast<float*>(smem + 2 * B_STAGE);  // [2][256] lse * log2(e); +inf for q >= L
-    float* sD = sL + 512;                                      // [2][256] delta / 8;     0 for q >= L
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 512);
-    uint64_t *full = bars, *empty = bars + 2, *s_ready = bars + 4, *p_ready = bars + 7, *c_free = bars + 10, *acc_ready = bars + 13,
-             *acc_free = bars + 14;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
-
-    const int lane = threadIdx.x & 31;
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
-    const int E = H * HD;
-    const int64_t ld3 = 3 * (int64_t)E;
-    const int n_local = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int G = 16 * n_local;  // column chunks: 4 units x 4 chunks per item
-
-    if (warp == B_WARP_TMA && elect_one()) {
-        tma_prefetch_desc(&tmQKV);
-        tma_prefetch_desc(&tmDO);
-    }
-    if (warp == B_WARP_MMA1) {
-        if (elect_one()) {
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&full[i], 2);  // TMA transaction bytes + the producer warp's lse / delta staging
-                mbar_init(&empty[i], 1);
-            }
-            for (int i = 0; i < 3; ++i) {
-                mbar_init(&s_ready[i], 1);
-                mbar_init(&p_ready[i], GROUP_WARPS);
-                mbar_init(&c_free[i], 1);
-            }
-            mbar_init(acc_ready, 1);
-            mbar_init(acc_free, DRAIN_WARPS);
-            fence_barrier_init();
-        }
-        __syncwarp();
-        tmem_alloc(tmem_ptr_smem, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    const uint32_t smem_lo = smem_u32(smem) >> 4;
-
-    // Register budgets per warpgroup, out of the 768 x 80 the launch gives the CTA (setmaxnreg only moves registers inside
-    // that pool): control 32, drain 96, math 88: 128 x 32 + 128 x 96 + 512 x 88 = 61 440.
-    if (warp >= B_WARP_DRAIN0) {
-        // =========================== accumulator drain: dQ / dV,dK rows -> dqkv (+ qkv bias gradient) ===========================
-        // A warpgroup of its own, so that no math warp ever waits for the last MMA2 of a unit: the accumulator is handed
-        // back as soon as its columns are in registers, the global stores and the column sums run behind the next unit.
-        setmaxnreg_inc<96>();
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + B_COL_ACC;
-        const int n_units = 4 * n_local;
-        for (int ug = 0; ug < n_units; ++ug) {
-            const int un = ug & 3;
-            const int it = blockIdx.x + (ug >> 2) * gridDim.x;
-            const int b = it / H, hd = it - b * H;
-            mbar_wait(acc_ready, ug & 1, 74);
-            tc_fence_after();
-            const int r = (un & 1) * 128 + row;  // query (dQ units) or key (dK/dV units)
-            const bool ok = r < L;
-            uint32_t a[32], a2[32];
-            auto release = [&]() {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_free);
-            };
-            auto put = [&](bf16* dst, float* dcol) {
-                if (ok) {
-                    store_32cols_bf16(dst, a, 1.f);
-                    store_32cols_bf16(dst + 32, a2, 1.f);
-                }
-                if (dbias != nullptr) {
-                    warp_colsum32_atomic(a, ok, dcol, lane);
-                    warp_colsum32_atomic(a2, ok, dcol + 32, lane);
-                }
-            };
-            bf16* drow = dqkv + ((int64_t)b * L + r) * ld3 + hd * HD;
-            tmem_ld_32x32b_x32(acc_addr, a);
-            tmem_ld_32x32b_x32(acc_addr + 32, a2);
-            tmem_ld_wait();
-            reg_fence(a);
-            reg_fence(a2);
-            if (un < 2) {
-                release();
-                put(drow, dbias + hd * HD);  // dQ
-            } else {
-                put(drow + 2 * E, dbias + 2 * E + hd * HD);  // dV (columns [0, 64) of the accumulator)
-                tmem_ld_32x32b_x32(acc_addr + 64, a);
-                tmem_ld_32x32b_x32(acc_addr + 96, a2);
-                tmem_ld_wait();
-                reg_fence(a);
-                reg_fence(a2);
-                release();
-                put(drow + E, dbias + E + hd * HD);  // dK (columns [64, 128))
-            }
-        }
-    } else if (warp >= B_WARP_TMA) {
-    setmaxnreg_dec<32>();
-    if (warp == B_WARP_TMA) {
-        // =========================== TMA producer (+ lse / delta staging) ===========================
-        for (int n = 0; n < n_local; ++n) {
-            const int it = blockIdx.x + n * gridDim.x;
-            const int b = it / H, hd = it - b * H;
-            const int s = n & 1;
-            mbar_wait(&empty[s], ((n >> 1) & 1) ^ 1, 70);
-            if (elect_one()) {
-                uint8_t* st = smem + s * B_STAGE;
-                mbar_arrive_expect_tx(&full[s], B_STAGE);
-#pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    const int r0 = h2 * BOX_ROWS;
-                    tma_load_3d(st + 0 * OPER_BYTES + r0 * 128, &tmQKV, &full[s], hd * HD, r0, b);
-                    tma_load_3d(st + 1 * OPER_BYTES + r0 * 128, &tmQKV, &full[s], E + hd * HD, r0, b);
-                    tma_load_3d(st + 2 * OPER_BYTES + r0 * 128, &tmQKV, &full[s], 2 * E + hd * HD, r0, b);
-                    tma_load_3d(st + 3 * OPER_BYTES + r0 * 128, &tmDO, &full[s], hd * HD, r0, b);
-                }
-            }
-            __syncwarp();
-            float lv[8], dv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int q = lane + 32 * i;
-                lv[i] = q < L ? __ldg(lse + (int64_t)it * L + q) : INFINITY;
-                dv[i] = q < L ? __ldg(delta + (int64_t)it * L + q) : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                sL[s * 256 + lane + 32 * i] = lv[i] * LOG2E;
-                sD[s * 256 + lane + 32 * i] = dv[i] * 0.125f;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-        }
-    } else if (warp == B_WARP_MMA1) {
-        // =========================== MMA1 issuer: S_c, dP_c three chunks ahead of the math ===========================
-        // chunk g = 16 n + 4 unit + c goes to chunk buffer g % 3, free again once MMA2(g-3) (other issuer) has completed.
-        const uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0), idesc16 = make_idesc_bf16(128, 16, 0, 0);
-        int cb = 0;
-        uint32_t ph = 0;
-        for (int g = 0; g < G; ++g) {
-            const int n = g >> 4, un = (g >> 2) & 3, c = g & 3, s = n & 1;
-            if ((g & 15) == 0) mbar_wait(&full[s], (n >> 1) & 1, 71);
-            mbar_wait(&c_free[cb], ph ^ 1, 79);  // passes at once for the first use of each buffer
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t base = smem_lo + ((s * B_STAGE) >> 4);
-                const uint32_t tile = (un & 1) * (TILE_BYTES >> 4);  // lanes = rows [128 (un & 1), +128) of the unit's operand
-                const uint32_t crow = c * 64 * 8;                    // chunk columns = rows [64 c, ...) of the other operand
-                uint32_t a1, b1, a2, b2;
-                if (un < 2) {  // S = Q_t K_c^T, dP = dO_t V_c^T
-                    a1 = base + OFF_Q + tile, b1 = base + OFF_K + crow, a2 = base + OFF_DO + tile, b2 = base + OFF_V + crow;
-                } else {       // S^T = K_j Q_c^T, dP^T = V_j dO_c^T
-                    a1 = base + OFF_K + tile, b1 = base + OFF_Q + crow, a2 = base + OFF_V + tile, b2 = base + OFF_DO + crow;
-                }
-                const uint32_t idesc = c == 3 ? idesc16 : idesc64;
-                const uint32_t d = tmem_base + cb * 128;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16_ss(d, make_desc((a1 | LBO_K) + 2 * k, DESC_HI), make_desc((b1 | LBO_K) + 2 * k, DESC_HI), idesc, k > 0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16_ss(d + 64, make_desc((a2 | LBO_K) + 2 * k, DESC_HI), make_desc((b2 | LBO_K) + 2 * k, DESC_HI), idesc, k > 0);
-                umma_commit(&s_ready[cb]);
-            }
-            __syncwarp();
-            if (++cb == 3) cb = 0, ph ^= 1;
-        }
-    } else if (warp == B_WARP_MMA2) {
-        // =========================== MMA2 issuer: accumulate from the packed operands the math warps left in TMEM ===========================
-        const uint32_t idesc2 = make_idesc_bf16(128, HD, 0, 1);
-        int cb = 0;
-        uint32_t ph = 0;
-        for (int g = 0; g < G; ++g) {
-            const int n = g >> 4, un = (g >> 2) & 3, c = g & 3, s = n & 1;
-            const int ug = g >> 2;
-            if (lane == 0) VB_STAMP(g, 0);
-            mbar_wait(&p_ready[cb], ph, 72);
-            if (c == 0) mbar_wait(acc_free, (ug & 1) ^ 1, 73);  // accumulator of unit ug-1 has been read out
-            if (lane == 0) VB_STAMP(g, 1);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t base = smem_lo + ((s * B_STAGE) >> 4);
-                const uint32_t crow = c * 64 * 8;
-                const int ksteps = c == 3 ? 1 : 4;  // 16 operand rows per k-step
-                const uint32_t acc = tmem_base + B_COL_ACC;
-                const uint32_t pbuf = tmem_base + cb * 128;
-                if (un < 2) {
-                    const uint32_t kmn = (base + OFF_K + crow) | LBO_MN;  // dQ_t += dS_c K_c
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k < ksteps)
-                            umma_bf16_ts(acc, pbuf + 64 + (k >> 1) * 32 + (k & 1) * 8, make_desc(kmn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));
-                } else {
-                    const uint32_t domn = (base + OFF_DO + crow) | LBO_MN, qmn = (base + OFF_Q + crow) | LBO_MN;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k < ksteps) {
-                            const uint32_t acol = (k >> 1) * 32 + (k & 1) * 8;
-                            umma_bf16_ts(acc, pbuf + acol, make_desc(domn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));           // dV_j += P^T dO_c
-                            umma_bf16_ts(acc + 64, pbuf + 64 + acol, make_desc(qmn + k * 128, DESC_HI), idesc2, (c > 0 || k > 0));  // dK_j += dS^T Q_c
-                        }
-                }
-                umma_commit(&c_free[cb]);  // chunk buffer reusable by MMA1(g+3)
-                if (c == 3) {
-                    umma_commit(acc_ready);
-                    // last MMA2 of the item; every MMA1 of the item completed before its math could run, so the stage is free
-                    if (un == 3) umma_commit(&empty[s]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) VB_STAMP(g, 2);
-            if (++cb == 3) cb = 0, ph ^= 1;
-        }
-    }
-    } else {
-        // =========================== math warps: group 0 takes even chunks, group 1 odd chunks ===========================
-        setmaxnreg_inc<88>();
-        const int grp = warp >> 3;
-        const int quarter = warp & 3, hf = (warp >> 2) & 1;
-        const int row = quarter * 32 + lane;
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        const float c = 0.125f * LOG2E;
-        const int c0 = hf * 32;
-
-        float lse_row = 0.f, dlt_row = 0.f;
-        for (int g = grp; g < G; g += 2) {
-            const int n = g >> 4, un = (g >> 2) & 3, cc = g & 3, s = n & 1, cb = g % 3;
-            const float* sLs = sL + s * 256;
-            const float* sDs = sD + s * 256;
-            if ((g & 15) == grp) mbar_wait(&full[s], (n >> 1) & 1, 76);  // this group's first chunk of the item: lse / delta staged
-            if (cc < 2 && un < 2) {
-                lse_row = sLs[(un & 1) * 128 + row];
-                dlt_row = sDs[(un & 1) * 128 + row];
-            }
-            const bool stp = (warp & 7) == 0 && lane == 0;
-            if (stp) VB_STAMP(g, 5);
-            mbar_wait(&s_ready[cb], (g / 3) & 1, 75);
-            if (stp) VB_STAMP(g, 6);
-            tc_fence_after();
-            const uint32_t sbuf = lane_addr + cb * 128, dbuf = sbuf + 64;
-            if (cc < 3) {
-                uint32_t sv[32], dv[32];
-                tmem_ld_32x32b_x32(sbuf + c0, sv);
-                tmem_ld_32x32b_x32(dbuf + c0, dv);
-                tmem_ld_wait();
-                reg_fence(sv);
-                reg_fence(dv);
-                if (un < 2) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float p0 = fast_ex2(fmaf(__uint_as_float(sv[2 * i]), c, -lse_row));
-                        const float p1 = fast_ex2(fmaf(__uint_as_float(sv[2 * i + 1]), c, -lse_row));
-                        pk[i] = pack_bf16x2(p0 * fmaf(__uint_as_float(dv[2 * i]), 0.125f, -dlt_row),
-                                            p1 * fmaf(__uint_as_float(dv[2 * i + 1]), 0.125f, -dlt_row));
-                    }
-                    tmem_st_x16(dbuf + c0, pk);  // dS packed in place of dP (own column range)
-                } else {
-                    uint32_t pp[16], pd[16];
-                    const float* lq = sLs + cc * 64 + c0;  // same address for the whole warp: smem broadcast
-                    const float* dq = sDs + cc * 64 + c0;
-#pragma unroll
-                    for (int gq = 0; gq < 8; ++gq) {
-                        const float4 l4 = lds128(lq + 4 * gq), d4 = lds128(dq + 4 * gq);
-                        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-                        float p[4], ds[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            p[i] = fast_ex2(fmaf(__uint_as_float(sv[4 * gq + i]), c, -lv[i]));
-                            ds[i] = p[i] * fmaf(__uint_as_float(dv[4 * gq + i]), 0.125f, -dl[i]);
-                        }
-                        pp[2 * gq] = pack_bf16x2(p[0], p[1]);
-                        pp[2 * gq + 1] = pack_bf16x2(p[2], p[3]);
-                        pd[2 * gq] = pack_bf16x2(ds[0], ds[1]);
-                        pd[2 * gq + 1] = pack_bf16x2(ds[2], ds[3]);
-                    }
-                    tmem_st_x16(sbuf + c0, pp);
-                    tmem_st_x16(dbuf + c0, pd);
-                }
-            } else if (hf == 0) {
-                // 16-column tail chunk (operand rows 192..207): handled by the first column-half warps only
-                uint32_t sv[16], dv[16];
-                tmem_ld_32x32b_x16(sbuf, sv);
-                tmem_ld_32x32b_x16(dbuf, dv);
-                tmem_ld_wait();
-                reg_fence(sv);
-                reg_fence(dv);
-                uint32_t pp[8], pd[8];
-                if (un < 2) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float p0 = fast_ex2(fmaf(__uint_as_float(sv[2 * i]), c, -lse_row));
-                        const float p1 = fast_ex2(fmaf(__uint_as_float(sv[2 * i + 1]), c, -lse_row));
-                        pd[i] = pack_bf16x2(p0 * fmaf(__uint_as_float(dv[2 * i]), 0.125f, -dlt_row),
-                                            p1 * fmaf(__uint_as_float(dv[2 * i + 1]), 0.125f, -dlt_row));
-                    }
-                    tmem_st_x8(dbuf, pd);
-                } else {
-                    const float* lq = sLs + 192;
-                    const float* dq = sDs + 192;
-#pragma unroll
-                    for (int gq = 0; gq < 4; ++gq) {
-                        const float4 l4 = lds128(lq + 4 * gq), d4 = lds128(dq + 4 * gq);
-                        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-                        float p[4], ds[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            p[i] = fast_ex2(fmaf(__uint_as_float(sv[4 * gq + i]), c, -lv[i]));
-                            ds[i] = p[i] * fmaf(__uint_as_float(dv[4 * gq + i]), 0.125f, -dl[i]);
-                        }
-                        pp[2 * gq] = pack_bf16x2(p[0], p[1]);
-                        pp[2 * gq + 1] = pack_bf16x2(p[2], p[3]);
-                        pd[2 * gq] = pack_bf16x2(ds[0], ds[1]);
-                        pd[2 * gq + 1] = pack_bf16x2(ds[2], ds[3]);
-                    }
-                    tmem_st_x8(sbuf, pp);
-                    tmem_st_x8(dbuf, pd);
-                }
-            }
-            if (stp) VB_STAMP(g, 7);
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_ready[cb]);
-            if (stp) VB_STAMP(g, 8);
-            if (stp) VB_STAMP(g, 9);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == B_WARP_MMA1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-#undef VB_STAMP
-}
 
 // =====================================================================================================
 // backward, key-domain schedule ("kd"): S and dP are computed ONCE per (key tile, query chunk), keys on the TMEM lanes
@@ -1678,9 +1314,6 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
     CUtensorMap tmQKV, tmDO;
     int rc = make_maps(&tmQKV, qkv, &tmDO, dout, batch, L, H);
     if (rc) return rc;
-    static bool done = false;
-    rc = set_smem(attention_bwd_persistent_kernel, B_SMEM, done);
-    if (rc) return rc;
     const int rows = batch * L;
     if (out != nullptr) {  // (nullptr: the caller already left delta in the workspace, e.g. from the proj-dgrad epilogue)
         attention_delta_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(out, dout, delta, rows, L, H);
@@ -1689,31 +1322,6 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
     const int n_items = batch * H;
     const int grid = n_items < num_sms() ? n_items : num_sms();
     static const bool dbg_on = getenv("VITB200_DBG_TIMING") != nullptr;  // development only
-    static const bool two_domain = []() {
-        const char* e = getenv("VITB200_ATTN_BWD");
-        return e != nullptr && e[0] == 'o';  // "old": the two-domain kernel (measurement / bisection)
-    }();
-    if (dbg_on && two_domain) {
-        long long* dbg = nullptr;
-        VB_CHECK_CUDA(cudaMallocManaged(&dbg, 64 * 16 * sizeof(long long)));
-        VB_CHECK_CUDA(cudaMemset(dbg, 0, 64 * 16 * sizeof(long long)));
-        attention_bwd_persistent_kernel<<<grid, B_THREADS, B_SMEM, stream>>>(tmQKV, tmDO, lse, delta, dqkv, dbias, L, H, n_items, dbg);
-        VB_CHECK_CUDA(cudaStreamSynchronize(stream));
-        const long long t0 = dbg[0];
-        printf("[bwd timing] j: mma{waitP< waitP> mma2> mma1>} - math{waitS< waitS> math> arrive> readout>}\n");
-        for (int g = 0; g < 64; ++g) {
-            printf("[bwd timing] %3d:", g + 32);
-            for (int i = 0; i < 10; ++i) printf(" %7lld", dbg[g * 16 + i] ? dbg[g * 16 + i] - t0 : -1);
-            printf("\n");
-        }
-        cudaFree(dbg);
-        return VB_OK;
-    }
-    if (two_domain) {
-        attention_bwd_persistent_kernel<<<grid, B_THREADS, B_SMEM, stream>>>(tmQKV, tmDO, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
-        VB_CHECK_LAUNCH();
-        return VB_OK;
-    }
     // key-domain kernel: K / V come in per key tile (128 and 80 rows), so they get their own boxes
     CUtensorMap tmKV0, tmKV1;
     const int64_t E = (int64_t)H * HD;
