@@ -125,3 +125,22 @@ def plasticity(model_name: str, pairs: int, batch: int, threads: int):
         done += n
     dt = time.perf_counter() - t0
     return pairs / dt, dt
+
+
+def loss_and_grads_on(device: str, model_name: str, state_dict: dict, x, y, n_classes: int = 10):
+    """The unmodified reference ViT on ``device`` (fp32, TF32 off) with the given weights: cross-entropy loss of one batch
+    and the gradient of every parameter, {name: tensor}. Used for the bench-scale parity check (batch 512: M = 100 864
+    token rows, split-K weight gradients over 100 864 tokens), which no CPU oracle finishes in seconds."""
+    import torch
+    import torch.nn.functional as F
+
+    build_model, _, _, _ = _import_reference()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = {"implementation": "vit", "model_name": model_name, "pretrained": False, "in21k": True, "finetuning": True, "n_classes": n_classes}
+    model = build_model(cfg, device=device)
+    model.load_state_dict(state_dict)
+    model.train()
+    loss = F.cross_entropy(model(x), y)
+    loss.backward()
+    return float(loss), {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
