@@ -1,5 +1,5 @@
 """bench.py on the CPU: the reference arm's JSON line (driven through the UNMODIFIED reference under baseline/_ref when it is
-installed; `unavailable` otherwise) carries the keys of the benchmark contract and the same `config` the B200 arm prints,
+installed; the oracle port otherwise) carries the keys of the benchmark contract and the same `config` the B200 arm prints,
 and the FLOP accounting of the estimator is self-consistent."""
 
 import json
@@ -44,13 +44,13 @@ def test_reference_arm_prints_the_contract_line():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference"
-    if "unavailable" in line:  # baseline/_ref not installed on this machine
-        assert isinstance(line["unavailable"], str) and line["unavailable"]
-        return
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["unit"] == "img/s" and line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 1
-    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    # "reference" when baseline/_ref is installed (the build container, the GPU box), "port" (the oracle) otherwise
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    if (ROOT / "baseline" / "_ref" / "vitef").is_dir():
+        assert line["cpu_baseline"]["kind"] == "reference"
     assert line["e2e"] == {"value": line["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # the same `config` object the B200 arm prints for this workload
     assert line["config"] == bench.finetune_config("base", 512, 1, [], 85806346, "strong")

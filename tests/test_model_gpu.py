@@ -381,11 +381,12 @@ def test_analysis_loop_writes_reference_distances_pkl(tmp_path):
     assert set(plast) == {"attn_norm", "attn", "ffn_norm", "ffn_fc1", "ffn_fc2"} and all(len(v) == arch.n_layers for v in plast.values())
 
 
-def test_decomposition_and_probes_api_tiny():
-    gold = load("tiny")
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_decomposition_and_probes_api(name):
+    gold = load(name)
     arch = arch_of(gold)
     sd = O.init_state_dict(arch, seed=gold["weights_seed"])
-    model = build("tiny", gold, arch, sd).eval()
+    model = build(name, gold, arch, sd).eval()
     x = O.synthetic_images(gold["batch"], arch, gold["x_seed"])
     probes = model.get_probes(x.to(DEV))
     assert list(probes) == list(gold["probes"])

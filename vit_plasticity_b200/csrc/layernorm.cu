@@ -4,6 +4,8 @@
 //     dgamma / dbeta in registers across a persistent row loop, one atomicAdd per column per block at the end.
 // Replaces nn.LayerNorm (reference: src/vitef/models/transformer/utils.py:293; call sites
 // architecture.py:347,349 and transformer/utils.py:396) and native_layer_norm_backward under autograd.
+#include <stdlib.h>
+
 #include "host_utils.h"
 #include "ptx.cuh"
 
@@ -503,7 +505,12 @@ extern "C" int vb_layernorm_fwd(const void* x, const float* gamma, const float* 
     VB_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 2048, "vb_layernorm_fwd: cols=%d must be a multiple of 8, <= 2048", cols);
     const int chunks = (cols / 8 + 31) / 32;
     int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    static const int blocks_per_sm = []() {
+        const char* e = getenv("VB_LN_FWD_BLOCKS_PER_SM");  // measurement knob
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? v : 8;
+    }();
+    if (grid > num_sms() * blocks_per_sm) grid = num_sms() * blocks_per_sm;
     VB_LN_DISPATCH(chunks, (layernorm_fwd_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(
                                static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y), mean, rstd, rows, cols, eps)));
     VB_CHECK_LAUNCH();
