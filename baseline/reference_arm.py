@@ -103,26 +103,35 @@ def finetune(model_name: str, batch: int, steps: int, warmup: int, components, t
     return batch / dt, dt, n_trainable
 
 
-def plasticity(model_name: str, pairs: int, batch: int, threads: int):
-    """BASELINE.json configs[0]: the reference estimator as apps/vit/analysis.py:216-233 runs it (get_decomposition on both
-    batches, distance per key) on ``pairs`` synthetic image pairs, fp32 on the CPU. Returns (pairs/s, seconds)."""
+def plasticity(model_name: str, pairs: int, batch: int, threads: int, device: str = "cpu"):
+    """BASELINE.json configs[0]: the reference estimator as apps/vit/analysis.py:203-233 runs it (pin + copy of both
+    batches, get_decomposition on each — every component output comes back on the host, architecture.py:385-418 —, then
+    per key the re-upload and distance) on ``pairs`` synthetic image pairs, fp32. Returns (pairs/s, seconds)."""
     import torch
 
     build_model, _, _, distance = _import_reference()
     torch.set_num_threads(threads)
-    model = _vit(build_model, model_name, "cpu")
+    model = _vit(build_model, model_name, device)
     model.eval()
     g = torch.Generator().manual_seed(0)
+    if device != "cpu":
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     done = 0
     while done < pairs:
         n = min(batch, pairs - done)
         x1, x2 = torch.randn(n, 3, 224, 224, generator=g), torch.randn(n, 3, 224, 224, generator=g)
+        if device != "cpu":
+            x1, x2 = x1.pin_memory(), x2.pin_memory()
+        x1, x2 = x1.to(device=device, non_blocking=True), x2.to(device=device, non_blocking=True)
         out1, out2 = model.get_decomposition(x1), model.get_decomposition(x2)
         dist = {}
-        for key in out1:
-            dist[key] = distance(out1[key], out2[key], reduction="none").numpy()
+        for key in list(out1.keys()):
+            z1, z2 = out1.pop(key).to(device), out2.pop(key).to(device)
+            dist[key] = distance(z1, z2, reduction="none").cpu().numpy()
         done += n
+    if device != "cpu":
+        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return pairs / dt, dt
 

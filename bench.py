@@ -699,6 +699,14 @@ def gpu_eager_block(ctx, args, comps):
         except Exception as exc:  # e.g. out of memory: the reference materialises two fp32 score tensors per layer
             out[name] = {"error": repr(exc)[:200]}
         torch.cuda.empty_cache()
+    try:  # the reference estimator as shipped, on this GPU: every component output crosses PCIe twice (analysis.py:216-226)
+        R.plasticity(args.model, 16, 16, os.cpu_count() or 1, device=str(ctx.dev))
+        v, dt = R.plasticity(args.model, 64, 16, os.cpu_count() or 1, device=str(ctx.dev))
+        out["estimator_as_shipped"] = {"value": round(v, 1), "unit": "pairs/s", "pairs": 64, "seconds": round(dt, 2),
+                                       "note": "get_decomposition x 2 (outputs to the host) + re-upload + distance per key, fp32, batches of 16"}
+    except Exception as exc:
+        out["estimator_as_shipped"] = {"error": repr(exc)[:200]}
+    torch.cuda.empty_cache()
     return out
 
 
