@@ -105,6 +105,12 @@ int vb_get_gemm_cta_pair(void);
  * (SMs held by a concurrent kernel such as an overlapped all-reduce) do not delay the launch. Same results either way. */
 void vb_set_gemm_scheduler(int dynamic);
 int vb_get_gemm_scheduler(void);
+/* Tile width of the CTA-pair kernels: 0 (default; env VB_GEMM_TILE_N=192|256 overrides) = chosen per launch: 192-column
+ * tiles where they save a wave of the persistent grid (the N = 768 GEMMs of a ViT-B block at <= 128 images per GPU: proj /
+ * fc2 forward with the residual epilogue, the fc1 / qkv dgrads), else 256; 192 / 256 = forced wherever the 192-column
+ * variant exists. Bit-identical results per output element (same k order). */
+void vb_set_gemm_tile_n(int tile_n);
+int vb_get_gemm_tile_n(void);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm (nn.LayerNorm, transformer/utils.py:293; used at architecture.py:347,349 and utils.py:396)
@@ -113,10 +119,14 @@ int vb_get_gemm_scheduler(void);
 int vb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                      int32_t rows, int32_t cols, float eps, vb_stream_t stream);
 /* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta accumulated (+=) into f32 [cols] when non-NULL.
- * `partial` is a caller workspace of vb_layernorm_bwd_workspace_bytes(cols) bytes. */
+ * `dres_colsum` (f32 [cols] or NULL; needs dres): += column sums of dres, taken while dres passes through the kernel. In a
+ * pre-norm block dres of the second norm's backward is the block's incoming gradient and dres of the first norm's backward
+ * is the gradient of the attention branch's output, so these are the bias gradients of the two Linear layers that write
+ * the residual stream (architecture.py:236,297) without a pass of their own.
+ * vb_layernorm_bwd_workspace_bytes is kept for callers of the first version of this interface and returns 0. */
 int64_t vb_layernorm_bwd_workspace_bytes(int32_t cols);
 int vb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                     const void* dres, void* dx, float* dgamma, float* dbeta, void* partial, int32_t rows,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, float* dres_colsum, int32_t rows,
                      int32_t cols, vb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

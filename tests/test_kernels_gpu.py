@@ -97,6 +97,41 @@ def test_gemm_pair_and_single_mappings_agree_bitwise():
     assert torch.equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("m", [1000, 12608 // 4, 300])
+def test_gemm_tile_192_agrees_bitwise_with_256(m):
+    """The 192-column tile variants (N = 768 GEMMs at few token rows: proj / fc2 forward with the residual epilogue, K-major
+    B staged as a 96-row box per CTA; fc1 / qkv dgrad, MN-major B staged as two 64-column boxes) keep the k order of every
+    output element: identical bits to the 256-column tiles, ragged last row block included; and both match fp32 torch."""
+    L = _lib()
+    lib = L.lib()
+    before, before_pair = lib.vb_get_gemm_tile_n(), lib.vb_get_gemm_cta_pair()
+    lib.vb_set_gemm_cta_pair(1)
+    try:
+        for n, k in ((768, 768), (768, 3072), (384, 320)):
+            a = _rand(m, k, seed=1).bfloat16()
+            w = _rand(n, k, seed=2, scale=0.05).bfloat16()  # forward weight [n_out = n, k_in = k]
+            bias = _rand(n, seed=3)
+            res = _rand(m, n, seed=4).bfloat16()
+            dy = _rand(m, k, seed=5).bfloat16()              # dgrad: dx [m, n] = dy [m, k] @ W [k, n], W stored [k, n]
+            wd = _rand(k, n, seed=6, scale=0.05).bfloat16()
+            outs = []
+            for tile in (256, 192):
+                lib.vb_set_gemm_tile_n(tile)
+                o_res = torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16)
+                o_dg = torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16)
+                L.gemm(a, w, m=m, n=n, k=k, epilogue=L.EPI_BF16_RESID, bias=bias, aux=res, out=o_res)
+                L.gemm(dy, wd, m=m, n=n, k=k, b_layout=1, epilogue=L.EPI_BF16, out=o_dg)
+                torch.cuda.synchronize()
+                outs.append((o_res, o_dg))
+            assert torch.equal(outs[0][0], outs[1][0]), (n, k)
+            assert torch.equal(outs[0][1], outs[1][1]), (n, k)
+            _report("gemm_tile192_resid", outs[1][0], a.float() @ w.float().T + bias + res.float(), atol=3e-2, rtol=1e-2)
+            _report("gemm_tile192_dgrad", outs[1][1], dy.float() @ wd.float(), atol=3e-2, rtol=1e-2)
+    finally:
+        lib.vb_set_gemm_tile_n(before)
+        lib.vb_set_gemm_cta_pair(before_pair)
+
+
 GEMM_SHAPES = [(128, 256, 64), (256, 256, 128), (384, 512, 256), (1000, 768, 768), (197 * 3, 2304, 768), (130, 136, 72)]
 
 
@@ -316,6 +351,32 @@ def test_layernorm_fwd_bwd(rows, cols):
     _report("ln_dx", dx, xf.grad + dres.float(), atol=3e-2, rtol=1e-2)
     _report("ln_dgamma", dg[None], gf.grad[None], atol=1e-2, rtol=1e-3)
     _report("ln_dbeta", db[None], bf.grad[None], atol=1e-2, rtol=1e-3)
+    # the same call also sums the columns of dres (the bias gradient of the Linear that wrote the residual stream): accumulates
+    # into its buffer, leaves every other output bit-identical, also with the parameter gradients switched off (frozen norm)
+    cs = torch.full((cols,), 0.5, device=DEV)
+    dg2, db2 = torch.zeros(cols, device=DEV), torch.zeros(cols, device=DEV)
+    dx2 = L.layernorm_bwd(dy, x, g, mean, rstd, dres=dres, dgamma=dg2, dbeta=db2, dres_colsum=cs)
+    cs_frozen = torch.zeros(cols, device=DEV)
+    dx3 = L.layernorm_bwd(dy, x, g, mean, rstd, dres=dres, dres_colsum=cs_frozen)
+    torch.cuda.synchronize()
+    assert torch.equal(dx2, dx) and torch.equal(dx3, dx)
+    _report("ln_dres_colsum", cs[None], (dres.float().sum(0) + 0.5)[None], atol=1e-3, rtol=1e-4)
+    _report("ln_dres_colsum_frozen", cs_frozen[None], dres.float().sum(0)[None], atol=1e-3, rtol=1e-4)
+    _report("ln_dgamma2", dg2[None], gf.grad[None], atol=1e-2, rtol=1e-3)
+
+
+def test_layernorm_bwd_colsum_many_rows():
+    """More rows than one pass of the persistent grid (every warp accumulates several rows into its shared-memory slice)."""
+    L = _lib()
+    rows, cols = 197 * 64, 768
+    x = _rand(rows, cols, seed=1).bfloat16()
+    g = _rand(cols, seed=2) * 0.5 + 1.0
+    _, mean, rstd = L.layernorm_fwd(x, g, torch.zeros(cols, device=DEV), 1e-12)
+    dy, dres = _rand(rows, cols, seed=4).bfloat16(), _rand(rows, cols, seed=5).bfloat16()
+    cs = torch.zeros(cols, device=DEV)
+    L.layernorm_bwd(dy, x, g, mean, rstd, dres=dres, dres_colsum=cs)
+    torch.cuda.synchronize()
+    _report("ln_dres_colsum_rows", cs[None], dres.double().sum(0).float()[None], atol=2e-2, rtol=1e-4)
 
 
 def test_layernorm_constant_row_is_finite():

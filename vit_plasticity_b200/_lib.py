@@ -75,6 +75,8 @@ SIGNATURES = {
     "vb_get_gemm_cta_pair": (c_int32, []),
     "vb_set_gemm_scheduler": (None, [c_int32]),
     "vb_get_gemm_scheduler": (c_int32, []),
+    "vb_set_gemm_tile_n": (None, [c_int32]),
+    "vb_get_gemm_tile_n": (c_int32, []),
     "vb_layernorm_fwd": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p],
@@ -272,12 +274,15 @@ def layernorm_fwd(x, gamma, beta, eps, *, want_stats=True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, dbeta=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, dbeta=None, dres_colsum=None):
+    """dx = dres + LN'(dy); dgamma / dbeta / dres_colsum (f32 [cols]) are accumulated into (+=) when given."""
     rows, cols = x.shape
     dx = torch.empty_like(x)
+    if dres_colsum is not None:
+        _req(dres_colsum, torch.float32, "dres_colsum")
     _check(
         lib().vb_layernorm_bwd(
-            dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(dres), dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), None, rows, cols, _stream()
+            dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(dres), dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(dres_colsum), rows, cols, _stream()
         ),
         "vb_layernorm_bwd",
     )

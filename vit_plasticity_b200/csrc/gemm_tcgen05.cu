@@ -88,7 +88,11 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKernelParams& p, int w
 }
 
 // EPI_T >= 0: the epilogue is fixed at compile time (the hot combinations); -1: taken from p.epi at run time.
-template <int A_MN, int B_MN, int G, int EPI_T, int DEEP>
+// BNT = tile width in columns: 256, or 192 (pairs only, N % 192 == 0) for the N = 768 GEMMs at few token rows: 50 x 3 tiles
+// of 256 columns are 2.03 waves on 74 CTA pairs (3 waves paid), 50 x 4 tiles of 192 columns are 2.7 waves of 3/4 the work.
+// Each CTA of a pair then stages 96 columns of B (K-major: a 96-row box; MN-major: two 64-column boxes, the upper half
+// of the second one unused) in the same 16 KB slot; the accumulators keep their 256-column stride in TMEM.
+template <int A_MN, int B_MN, int G, int EPI_T, int DEEP, int BNT = BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
@@ -99,6 +103,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     using Cfg = GemmCfg<G, DEEP>;
     constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int STAGING = Cfg::STAGING_BYTES, NBUF = STAGING / 2048;
+    static_assert(BNT == BN || (BNT == 192 && G == 2 && (EPI_T == VB_EPI_BF16 || EPI_T == VB_EPI_BF16_RESID)),
+                  "tile width: 256, or 192 for the CTA-pair kernels of the plain / residual bf16 epilogues");
+    constexpr int BHALF = BNT / 2;   // columns per epilogue warp
+    constexpr int NCH = BHALF / 32;  // 32-column chunks per epilogue warp and tile
+    // bytes one CTA's producer puts into a stage (the MN-major B boxes are 64 columns wide: 96 columns take two)
+    constexpr int B_LOAD_BYTES = B_MN == 0 ? (BNT / G) * BK * 2 : ((BNT / G + 63) / 64) * 64 * BK * 2;
+    constexpr int STAGE_TX_BYTES = A_STAGE_BYTES + B_LOAD_BYTES;
     uint8_t* staging_base = smem + STAGES * STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + EPI_WARPS * STAGING);
     uint64_t* full_bar = bars;                       // [STAGES]  TMA -> MMA (G = 2: the leader's, fed by both CTAs)
@@ -213,13 +224,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         TileIter ti = {unit, 0, 0};
         for (int w = next_tile(ti); w >= 0; w = next_tile(ti)) {
             const WorkItem it = decode_work<G>(p, w, rank);
-            const int n0 = it.n_blk * BN + rank * (BN / G);  // this CTA's share of the B tile
+            const int n0 = it.n_blk * BNT + rank * (BNT / G);  // this CTA's share of the B tile
             for (int kb = it.kb0; kb < it.kb1; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                 uint8_t* sa = smem + stage * STAGE_BYTES;
                 uint8_t* sb = sa + A_STAGE_BYTES;
                 if (elect_one()) {
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES * G);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], STAGE_TX_BYTES * G);
                     if (A_MN == 0) {
                         load(sa, &tmA, &full_bar[stage], kb * BK, it.m_blk * BM);
                     } else {
@@ -231,7 +242,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         load(sb, &tmB, &full_bar[stage], kb * BK, n0);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BN / G / 64; ++i)
+                        for (int i = 0; i < (BNT / G + 63) / 64; ++i)
                             load(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
                     }
                 }
@@ -244,7 +255,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1 && rank == 0) {
         // =========================== MMA issuer (leader CTA only when G = 2) ===========================
-        constexpr uint32_t idesc = make_idesc_bf16(BM * G, BN, A_MN, B_MN);
+        constexpr uint32_t idesc = make_idesc_bf16(BM * G, BNT, A_MN, B_MN);
         // descriptor = constant high word (SBO 1024 B, version 1, SWIZZLE_128B) + low word (address, LBO)
         constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
         constexpr uint32_t lbo_a = A_MN == 0 ? 16u : (64u * BK * 2u), lbo_b = B_MN == 0 ? 16u : (64u * BK * 2u);
@@ -330,12 +341,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // =========================== epilogue ===========================
         setmaxnreg_inc<224>();
-        // Per tile each warp drains a 32-row x 128-column block of the accumulator in four 32-column chunks. The TMEM load
+        // Per tile each warp drains a 32-row x 128-column block of the accumulator in four 32-column chunks (BNT = 192: 96
+        // columns, three chunks). The TMEM load
         // of chunk c + 1 is in flight while chunk c is processed (two register buffers), and the accumulator is handed back
         // to the MMA warp as soon as the last load has landed, before that chunk's math and stores.
         const int ew = warp - EPI_FIRST_WARP;
         const int q = warp & 3;   // TMEM lane quarter this warp may access
-        const int hf = ew >> 2;   // which 128-column half of the tile
+        const int hf = ew >> 2;   // which half of the tile's columns
         uint8_t* stg = staging_base + ew * STAGING;
         const int epi = EPI_T >= 0 ? EPI_T : p.epi;
         const bool has_aux = (epi == VB_EPI_BF16_RESID || epi == VB_EPI_BF16_DGELU || epi == VB_EPI_BF16_MULAUX || epi == VB_EPI_BF16_ROWDOT);
@@ -353,7 +365,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tma_store_wait_read<1>();
                 uint64_t* bar = my_aux_bar + (t & 3);
                 mbar_arrive_expect_tx(bar, 2048);
-                tma_load_2d(stg + (t & 3) * 2048, &tmAux, bar, wi.n_blk * BN + hf * 128 + c * 32, wi.m_blk * BM + q * 32);
+                tma_load_2d(stg + (t & 3) * 2048, &tmAux, bar, wi.n_blk * BNT + hf * BHALF + c * 32, wi.m_blk * BM + q * 32);
             }
             __syncwarp();
         };
@@ -372,7 +384,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const WorkItem nxt_it = (AUX_TMA && have_next) ? decode_work<G>(p, w_next, rank) : it;
             const int row0 = it.m_blk * BM + q * 32;
             const int row = row0 + lane;
-            const int colbase = it.n_blk * BN + hf * 128;
+            const int colbase = it.n_blk * BNT + hf * BHALF;
             const bool row_ok = row < p.M;
 
             uint4 aux_cur[4], aux_nxt[4];
@@ -392,7 +404,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // per-chunk loads above hit L2 (~300 cycles) instead of HBM (~1500), which had made the short-K
                 // residual / GELU' epilogues latency-bound (proj forward: 136 us against 93 us without epilogue).
                 const WorkItem nx = decode_work<G>(p, w_next, rank);
-                const int nrow = nx.m_blk * BM + q * 32 + lane, ncol = nx.n_blk * BN + hf * 128;
+                const int nrow = nx.m_blk * BM + q * 32 + lane, ncol = nx.n_blk * BNT + hf * BHALF;
                 if (nrow < p.M && ncol < p.N) {
                     const bf16* pa = p.aux + (long long)nrow * p.ld_aux + ncol;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
@@ -405,7 +417,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
             float sumsq_local = 0.f;
             float rowdot = 0.f;  // ROWDOT: this row's partial sum over the current 64-column group (two chunks)
-            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + hf * 128;
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + hf * BHALF;
 
             // one 32-column chunk, accumulator values in v (as loaded from TMEM)
             auto process = [&](uint32_t(&v)[32], const int c) {
@@ -414,10 +426,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (AUX_TMA) {
                     // the aux operand of the chunk after next; then wait for this chunk's (every chunk is requested and
                     // awaited, also one that lies outside the matrix: the TMA unit zero-fills it)
-                    if (c < 2)
+                    if (c + 2 < NCH)
                         request_aux(it, c + 2, tchunk + 2);
                     else if (have_next)
-                        request_aux(nxt_it, c - 2, tchunk + 2);
+                        request_aux(nxt_it, c + 2 - NCH, tchunk + 2);
                     mbar_wait(my_aux_bar + (tchunk & 3), (tchunk >> 2) & 1, 5);
                 }
                 ++tchunk;
@@ -601,16 +613,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t va[32], vb[32];
             tmem_ld_32x32b_x32(tacc, va);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (!AUX_TMA && c < 3) load_aux(aux_nxt, colbase + c * 32 + 32);
+            for (int c = 0; c < NCH; ++c) {
+                if (!AUX_TMA && c < NCH - 1) load_aux(aux_nxt, colbase + c * 32 + 32);
                 if ((c & 1) == 0) {
                     tmem_ld_wait_x32(va);
-                    if (c < 3) tmem_ld_32x32b_x32(tacc + (c + 1) * 32, vb);
+                    if (c < NCH - 1) tmem_ld_32x32b_x32(tacc + (c + 1) * 32, vb);
                 } else {
                     tmem_ld_wait_x32(vb);
-                    if (c < 3) tmem_ld_32x32b_x32(tacc + (c + 1) * 32, va);
+                    if (c < NCH - 1) tmem_ld_32x32b_x32(tacc + (c + 1) * 32, va);
                 }
-                if (c == 3) {
+                if (c == NCH - 1) {
                     // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp now
                     tc_fence_before();
                     __syncwarp();
@@ -661,13 +673,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-template <int A_MN, int B_MN, int G, int EPI_T, int DEEP>
+template <int A_MN, int B_MN, int G, int EPI_T, int DEEP, int BNT = BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                        const CUtensorMap& tmAux, const GemmKernelParams& p, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     VB_CHECK_CUDA(cudaGetDevice(&dev));
-    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, G, EPI_T, DEEP>;
+    auto kern = gemm_tcgen05_kernel<A_MN, B_MN, G, EPI_T, DEEP, BNT>;
     constexpr int GEMM_SMEM_BYTES = GemmCfg<G, DEEP>::SMEM_BYTES;
     if (dev < 64 && !attr_set[dev]) {
         VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -752,10 +764,24 @@ static int cta_pair_enabled() {
     return g_cta_pair;
 }
 
+// Tile width of the CTA-pair kernels: 0 = chosen per launch (192 where it saves a wave, see vb_gemm_bf16), 192 / 256 = forced
+// wherever a 192-column variant exists (tests, A/B measurements). Default from VB_GEMM_TILE_N (0 if unset).
+static int g_tile_n = -1;
+static int tile_n_mode() {
+    if (g_tile_n < 0) {
+        const char* e = getenv("VB_GEMM_TILE_N");
+        const int v = e ? atoi(e) : 0;
+        g_tile_n = (v == 192 || v == 256) ? v : 0;
+    }
+    return g_tile_n;
+}
+
 }  // namespace vb
 
 extern "C" void vb_set_gemm_cta_pair(int mode) { vb::g_cta_pair = (mode >= 0 && mode <= 3) ? mode : 1; }
 extern "C" int vb_get_gemm_cta_pair(void) { return vb::cta_pair_enabled(); }
+extern "C" void vb_set_gemm_tile_n(int tile_n) { vb::g_tile_n = (tile_n == 192 || tile_n == 256) ? tile_n : 0; }
+extern "C" int vb_get_gemm_tile_n(void) { return vb::tile_n_mode(); }
 extern "C" void vb_set_gemm_scheduler(int dynamic) { vb::g_dynamic = dynamic ? 1 : 0; }
 extern "C" int vb_get_gemm_scheduler(void) { return vb::dynamic_enabled(); }
 
@@ -773,7 +799,20 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     const int epi = a->epilogue;
     // a CTA pair per 256 x 256 tile whenever there is more than one 128-row block to pair up
     const int G = (cta_pair_enabled() != 0 && a->m > BM) ? 2 : 1;
-    const int m_tiles = (a->m + BM * G - 1) / (BM * G), n_tiles = (a->n + BN - 1) / BN, k_blocks = (a->k + BK - 1) / BK;
+    const int m_tiles = (a->m + BM * G - 1) / (BM * G), k_blocks = (a->k + BK - 1) / BK;
+    // Tile width. The N = 768 GEMMs of a ViT-B block (proj / fc2 forward, the fc1 / qkv dgrads) have 3 tiles of 256 columns
+    // per row block: at 64 images per GPU that is 150 tiles = 2.03 waves on 74 pairs, a third of the launch spent on the last
+    // 3 tiles. 192-column tiles (4 per row block) cost ~0.78 of a 256-column tile each; they are taken when the waves they
+    // need are cheaper by more than 3 % (batch 64: 3 x 0.78 against 3; batch 512: 22 x 0.78 against 16, so 256 stays).
+    int bnt = BN;
+    const bool has192 = G == 2 && a->a_layout == 0 && a->n % 192 == 0 &&
+                        ((a->b_layout == 0 && epi == VB_EPI_BF16_RESID) || (a->b_layout == 1 && epi == VB_EPI_BF16 && a->out_colsum == nullptr));
+    if (has192) {
+        const int units = num_sms() / G;
+        const int waves256 = (m_tiles * ((a->n + BN - 1) / BN) + units - 1) / units, waves192 = (m_tiles * (a->n / 192) + units - 1) / units;
+        if (tile_n_mode() == 192 || (tile_n_mode() == 0 && 0.78 * waves192 < 0.97 * waves256)) bnt = 192;
+    }
+    const int n_tiles = (a->n + bnt - 1) / bnt;
     int split_k = a->split_k;
     if (split_k <= 0) {
         // auto (VB_EPI_F32_ADD only): the smallest split whose work items fill >= 90 % of the CTAs / pairs of its last
@@ -824,7 +863,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
                                 CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (a->b_layout == 0)
-        rc = make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, a->k, a->n, a->ldb * 2, BK, BN / G,
+        rc = make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, a->k, a->n, a->ldb * 2, BK, bnt / G,
                                 CU_TENSOR_MAP_SWIZZLE_128B);
     else
         rc = make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, a->n, a->k, a->ldb * 2, 64, BK,
@@ -891,6 +930,13 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     } while (0)
     const int al = a->a_layout, bl = a->b_layout;
     const int deep_mode = cta_pair_enabled() == 2 ? 0 : (cta_pair_enabled() == 3 ? 1 : -1);
+    if (bnt == 192) {
+        if (bl == 0) {
+            if (a->k >= 2048) return launch_gemm<0, 0, 2, VB_EPI_BF16_RESID, 0, 192>(tmA, tmB, tmC, tmC2, tmAux, p, stream);
+            return launch_gemm<0, 0, 2, VB_EPI_BF16_RESID, 1, 192>(tmA, tmB, tmC, tmC2, tmAux, p, stream);
+        }
+        return launch_gemm<0, 1, 2, VB_EPI_BF16, 0, 192>(tmA, tmB, tmC, tmC2, tmAux, p, stream);
+    }
     if (G == 2) {
         if (al == 0 && bl == 0) {
             if (epi == VB_EPI_BF16) VB_LAUNCH_PAIR(0, 0, VB_EPI_BF16, 0);

@@ -102,6 +102,33 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma
     }
 }
 
+// Column sums of the residual gradient (dres) on the way through the backward kernels: dres of LN2's backward is the block's
+// incoming gradient (its column sums are fc2's bias gradient), dres of LN1's backward is the gradient of the attention
+// branch's output (the output projection's bias gradient), so the 24 stand-alone column-sum passes per step (each a full
+// read of a [tokens, E] tensor) disappear. Partials live in shared memory, not registers (the dgamma / dbeta partials already
+// fill the register budget of two CTAs per SM): every warp owns a slice laid out [chunk half][lane] as float4, so its
+// read-modify-write per row is conflict-free and needs no synchronisation; one block reduction + atomics at the end.
+__device__ __forceinline__ void accumulate_dres(float4* my_dr, int i, int lane, const float (&r8)[8]) {
+    float4 a0 = my_dr[(2 * i) * 32 + lane], a1 = my_dr[(2 * i + 1) * 32 + lane];
+    a0.x += r8[0], a0.y += r8[1], a0.z += r8[2], a0.w += r8[3];
+    a1.x += r8[4], a1.y += r8[5], a1.z += r8[6], a1.w += r8[7];
+    my_dr[(2 * i) * 32 + lane] = a0;
+    my_dr[(2 * i + 1) * 32 + lane] = a1;
+}
+template <int CHUNKS>
+__device__ __forceinline__ void reduce_dres(const float4* sdr4, float* __restrict__ dres_colsum, int cols) {
+    __syncthreads();
+    const float* s = reinterpret_cast<const float*>(sdr4);
+    for (int idx = threadIdx.x; idx < CHUNKS * 256; idx += LN_WARPS * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) t += s[w * CHUNKS * 256 + idx];
+        const int e = idx & 3, ln = (idx >> 2) & 31, ih = idx >> 7;  // ih = 2 * chunk slot + half
+        const int col = ((ih >> 1) * 32 + ln) * 8 + (ih & 1) * 4 + e;
+        if (col < cols) atomicAdd(dres_colsum + col, t);
+    }
+}
+
 // Backward: persistent warps, gamma in shared memory, dgamma / dbeta partials in registers across the row loop.
 // Two CTAs (16 warps) per SM, <= 128 registers: each warp has the 9 independent 128-bit loads of its row in flight and
 // the other 15 warps cover their latency (the earlier one-CTA/SM version with a register-prefetched next row reached
@@ -110,12 +137,17 @@ template <int CHUNKS>
 __global__ void __launch_bounds__(LN_WARPS * 32, 2)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
-                     bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols) {
+                     bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dres_colsum, int rows, int cols) {
     __shared__ float red[LN_WARPS][32 * 8 + 1];
     __shared__ float sgamma[CHUNKS * 256];
+    extern __shared__ float4 sdr4[];  // dres_colsum only: [LN_WARPS][CHUNKS * 2][32 lanes] float4 partial column sums of dres
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = cols >> 3;
     for (int i = threadIdx.x; i < CHUNKS * 256; i += LN_WARPS * 32) sgamma[i] = i < cols ? __ldg(gamma + i) : 0.f;
+    float4* my_dr = sdr4 + warp * (CHUNKS * 64);  // this warp's slice: no synchronisation inside the row loop
+    if (dres_colsum != nullptr)
+        for (int k = lane; k < CHUNKS * 64; k += 32) my_dr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     float dg[CHUNKS][8], db[CHUNKS][8];
 #pragma unroll
@@ -176,6 +208,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
                 const float4 g1 = *reinterpret_cast<const float4*>(sgamma + c * 8 + 4);
                 const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
                 uint32_t o[4];
+                float r8[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float2 fx = unpack_bf16x2(wx[j]);
@@ -183,11 +216,15 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
                     const float2 fr = unpack_bf16x2(wr[j]);  // zeros when there is no residual gradient
                     const float h0 = (fx.x - mu) * rs, h1 = (fx.y - mu) * rs;
                     o[j] = pack_bf16x2(rs * (fd.x * g[2 * j] - s1 - h0 * s2) + fr.x, rs * (fd.y * g[2 * j + 1] - s1 - h1 * s2) + fr.y);
+                    r8[2 * j] = fr.x;
+                    r8[2 * j + 1] = fr.y;
                 }
                 dxr[c] = make_uint4(o[0], o[1], o[2], o[3]);
+                if (dres_colsum != nullptr) accumulate_dres(my_dr, i, lane, r8);
             }
         }
     }
+    if (dres_colsum != nullptr) reduce_dres<CHUNKS>(sdr4, dres_colsum, cols);
     if (dgamma == nullptr && dbeta == nullptr) return;  // frozen norm: parameter gradients not needed
     // block reduction of the per-warp partials, one chunk-slot at a time, then one atomic per column
     for (int pass = 0; pass < 2; ++pass) {
@@ -216,12 +253,17 @@ template <int CHUNKS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_wide_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
-                     bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols) {
+                     bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dres_colsum, int rows, int cols) {
     __shared__ float red[LN_WARPS][32 * 8 + 1];
     __shared__ float sgamma[CHUNKS * 256];
+    extern __shared__ float4 sdr4[];  // dres_colsum only: [LN_WARPS][CHUNKS * 2][32 lanes] float4 partial column sums of dres
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = cols >> 3;
     for (int i = threadIdx.x; i < CHUNKS * 256; i += LN_WARPS * 32) sgamma[i] = i < cols ? __ldg(gamma + i) : 0.f;
+    float4* my_dr = sdr4 + warp * (CHUNKS * 64);  // this warp's slice: no synchronisation inside the row loop
+    if (dres_colsum != nullptr)
+        for (int k = lane; k < CHUNKS * 64; k += 32) my_dr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     float dg[CHUNKS][8], db[CHUNKS][8];
 #pragma unroll
@@ -290,13 +332,17 @@ layernorm_bwd_wide_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
             if (c < nchunks) {
                 const uint32_t wr[4] = {cr[i].x, cr[i].y, cr[i].z, cr[i].w};
                 uint32_t o[4];
+                float r8[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float2 fr = unpack_bf16x2(wr[j]);  // zeros when there is no residual gradient
                     o[j] = pack_bf16x2(rs * (gy[i][2 * j] - s1 - xh[i][2 * j] * s2) + fr.x,
                                        rs * (gy[i][2 * j + 1] - s1 - xh[i][2 * j + 1] * s2) + fr.y);
+                    r8[2 * j] = fr.x;
+                    r8[2 * j + 1] = fr.y;
                 }
                 dxr[c] = make_uint4(o[0], o[1], o[2], o[3]);
+                if (dres_colsum != nullptr) accumulate_dres(my_dr, i, lane, r8);
             }
         }
 #pragma unroll
@@ -308,6 +354,7 @@ layernorm_bwd_wide_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ 
         cmu = nmu;
         crs = nrs;
     }
+    if (dres_colsum != nullptr) reduce_dres<CHUNKS>(sdr4, dres_colsum, cols);
     if (dgamma == nullptr && dbeta == nullptr) return;  // frozen norm: parameter gradients not needed
     // block reduction of the per-warp partials, one chunk-slot at a time, then one atomic per column
     for (int pass = 0; pass < 2; ++pass) {
@@ -523,25 +570,32 @@ extern "C" int64_t vb_layernorm_bwd_workspace_bytes(int32_t cols) {
 }
 
 extern "C" int vb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                                const void* dres, void* dx, float* dgamma, float* dbeta, void* partial, int32_t rows,
+                                const void* dres, void* dx, float* dgamma, float* dbeta, float* dres_colsum, int32_t rows,
                                 int32_t cols, vb_stream_t stream_) {
     using namespace vb;
-    (void)partial;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(dres_colsum == nullptr || dres != nullptr, "vb_layernorm_bwd: dres_colsum needs dres");
     VB_CHECK_ARG(dy && x && gamma && mean && rstd && dx, "vb_layernorm_bwd: null pointer");
     VB_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 2048, "vb_layernorm_bwd: cols=%d must be a multiple of 8, <= 2048", cols);
     const int chunks = (cols / 8 + 31) / 32;
     int grid = (rows + LN_WARPS - 1) / LN_WARPS;
     const int max_grid = num_sms() * 2;
     if (grid > max_grid) grid = max_grid;
+    if (dres_colsum != nullptr && chunks > 4) {
+        // rows wider than 1024 columns: the shared-memory partials would need the > 48 KB opt-in; take the separate pass
+        const int rc = vb_colsum_bf16(dres, cols, dres_colsum, rows, cols, stream_);
+        if (rc != VB_OK) return rc;
+        dres_colsum = nullptr;
+    }
+    const size_t dyn = dres_colsum != nullptr ? sizeof(float) * LN_WARPS * chunks * 256 : 0;
     if (chunks <= 3) {
-        VB_LN_DISPATCH(chunks, (layernorm_bwd_kernel < C <= 3 ? C : 1 > <<<grid, LN_WARPS * 32, 0, stream>>>(
+        VB_LN_DISPATCH(chunks, (layernorm_bwd_kernel < C <= 3 ? C : 1 > <<<grid, LN_WARPS * 32, dyn, stream>>>(
                                    static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd,
-                                   static_cast<const bf16*>(dres), static_cast<bf16*>(dx), dgamma, dbeta, rows, cols)));
+                                   static_cast<const bf16*>(dres), static_cast<bf16*>(dx), dgamma, dbeta, dres_colsum, rows, cols)));
     } else {
-        VB_LN_DISPATCH(chunks, (layernorm_bwd_wide_kernel<C><<<grid, LN_WARPS * 32, 0, stream>>>(
+        VB_LN_DISPATCH(chunks, (layernorm_bwd_wide_kernel<C><<<grid, LN_WARPS * 32, dyn, stream>>>(
                                    static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd,
-                                   static_cast<const bf16*>(dres), static_cast<bf16*>(dx), dgamma, dbeta, rows, cols)));
+                                   static_cast<const bf16*>(dres), static_cast<bf16*>(dx), dgamma, dbeta, dres_colsum, rows, cols)));
     }
     VB_CHECK_LAUNCH();
     return VB_OK;

@@ -162,6 +162,9 @@ class DataParallel(nn.Module):
 
     def _launch(self, b: int) -> None:
         self._launched[b] = True
+        from . import ops
+
+        ops.side_join()  # weight gradients enqueued on the side stream land in this bucket too
         if self.world > 1:
             self._handles.append(dist.all_reduce(self.buckets[b], op=self._op, group=self.group, async_op=True))
 

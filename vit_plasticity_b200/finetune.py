@@ -381,12 +381,17 @@ def train_step(model, optimizer, batches, grad_clip: float | None, scheduler=Non
     # overlapped buckets would be reduced during the first backward and later micro-batches would add un-reduced
     # gradients on top of (and racing with) the collective.
     syncer = model if hasattr(model, "require_grad_sync") else None
-    for i, (x, y) in enumerate(batches):
-        if syncer is not None:
-            syncer.require_grad_sync = i == acc - 1
-        preds = model(x)
-        loss = F.cross_entropy(preds, y) / acc
-        loss.backward()
+    # weight / bias gradients that accumulate in place into the arena run on a side stream during backward (their tail
+    # waves and the activation-gradient chain's fill each other's idle SMs); joined when the block is left
+    from . import ops
+
+    with ops.wgrad_overlap(isinstance(optimizer, FusedSGD)):
+        for i, (x, y) in enumerate(batches):
+            if syncer is not None:
+                syncer.require_grad_sync = i == acc - 1
+            preds = model(x)
+            loss = F.cross_entropy(preds, y) / acc
+            loss.backward()
     if after_backward is not None:
         after_backward()
     if isinstance(optimizer, FusedSGD):
@@ -442,7 +447,12 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         before = L.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # captured on a high-priority stream: the kernel nodes of the step's main chain keep that priority, so they get the
+        # SMs before the weight-gradient kernels of the (default-priority) side stream whenever both are runnable
+        import os
+
+        hp = os.environ.get("VB_GRAPH_PRIORITY", "1") != "0"
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(device=dev, priority=-1) if hp else None):
             self.out = train_step(self.model, self.optimizer, self.static, self.grad_clip, scheduler=None, after_backward=self.after_backward)
         self.launches_per_step = L.launch_count() - before
 

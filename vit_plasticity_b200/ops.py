@@ -28,6 +28,7 @@ from . import _lib as L
 
 NUM_SMS = 148
 _FUSED_DELTA = os.environ.get("VB_FUSED_DELTA", "1") != "0"  # measurement switch: 0 = stand-alone delta pass
+_FUSED_BIAS = os.environ.get("VB_FUSED_BIAS", "1") != "0"  # measurement switch: 0 = stand-alone column sums for proj / fc2 bias
 
 # --------------------------------------------------------------------------------------------------
 # bf16 shadow weights
@@ -98,6 +99,93 @@ def grad_done(p) -> None:
             obj._on_grad(p)
 
 
+# --------------------------------------------------------------------------------------------------
+# weight gradients on a side stream
+# --------------------------------------------------------------------------------------------------
+# In backward, dW = dy^T x and the bias column sums depend only on tensors the activation-gradient chain has already
+# produced, and nothing downstream reads them before the optimizer step. With ``wgrad_overlap`` on (finetune.train_step
+# turns it on around backward) they are enqueued on a second stream: every kernel on this path is persistent and sized
+# to all 148 SMs, so a kernel of one stream starts on the SMs the other stream's kernel frees during its last, partial
+# wave (at 64 images per GPU the 2.03- and 6.08-wave GEMMs of the strong-scaling split lose up to a third of a launch to
+# that tail). Only gradients accumulated in place into a persistent arena slot take this route (nothing is returned to
+# autograd, which would consume it on the main stream). Operands are kept alive until the main stream has waited for
+# the side stream's event of ``lag`` blocks ago, so the caching allocator cannot hand their memory to a later kernel
+# that might overtake the side stream; the same event waits are what a CUDA-graph capture records as dependencies.
+class _Side:
+    enabled = False
+    lag = int(os.environ.get("VB_WGRAD_LAG", "1"))
+    streams: dict = {}
+    keep: list = []  # operands of side-stream kernels enqueued since the last fence
+    pending: list = []  # [(event, operands)] of finished blocks, oldest first
+    dirty = False
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    s = _Side.streams.get(device.index)
+    if s is None:
+        s = _Side.streams[device.index] = torch.cuda.Stream(device=device)
+    return s
+
+
+class wgrad_overlap:
+    """Context manager: weight / bias gradients that accumulate in place run on the side stream inside the block.
+    Leaving the block joins the side stream (the main stream waits for everything enqueued on it)."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled and os.environ.get("VB_WGRAD_STREAM", "1") != "0"
+
+    def __enter__(self):
+        self.prev = _Side.enabled
+        _Side.enabled = self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        _Side.enabled = self.prev
+        side_join()
+        return False
+
+
+def _on_side(fn, *operands) -> bool:
+    """Run ``fn`` (kernel launches) on the side stream, ordered after everything enqueued on the current stream so
+    far. Returns False (nothing done) when the overlap is off or the launches are being timed one by one."""
+    if not _Side.enabled or L.GEMM_EVENTS is not None or not operands[0].is_cuda:
+        return False
+    main = torch.cuda.current_stream(operands[0].device)
+    side = _side_stream(operands[0].device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        fn()
+    _Side.keep.extend(operands)
+    _Side.dirty = True
+    return True
+
+
+def side_fence() -> None:
+    """End of one block's backward: mark the side stream and make the main stream wait for the mark of ``lag`` blocks
+    ago (whose operands may then be released)."""
+    if _Side.dirty:
+        dev = _Side.keep[0].device
+        ev = torch.cuda.Event()
+        ev.record(_side_stream(dev))
+        _Side.pending.append((ev, _Side.keep, dev))
+        _Side.keep = []
+        _Side.dirty = False
+    while len(_Side.pending) > _Side.lag:
+        ev, held, dev = _Side.pending.pop(0)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        held.clear()
+
+
+def side_join() -> None:
+    """The main stream waits for everything on the side stream (before the optimizer step, a gradient all-reduce, or
+    the end of a graph capture)."""
+    lag, _Side.lag = _Side.lag, 0
+    try:
+        side_fence()
+    finally:
+        _Side.lag = lag
+
+
 def _f32c(p: torch.Tensor | None) -> torch.Tensor | None:
     if p is None:
         return None
@@ -153,20 +241,28 @@ def linear_wgrad(dy, x, shape, param=None):
     k_in = x.shape[1]
     tgt = grad_target(param)
     dw = tgt.view(n_out, k_in) if tgt is not None else torch.zeros(n_out, k_in, device=dy.device, dtype=torch.float32)
-    L.gemm(dy, x, m=n_out, n=k_in, k=tokens, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=0)  # 0: the library picks the split that fills the SMs
+
+    def launch():
+        L.gemm(dy, x, m=n_out, n=k_in, k=tokens, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, out=dw, split_k=0)  # 0: the library picks the split that fills the SMs
+
     if tgt is not None:
+        if not _on_side(launch, dy, x):
+            launch()
         grad_done(param)
         return None
+    launch()
     return dw.view(shape)
 
 
 def bias_grad(dy, param=None):
     tgt = grad_target(param)
     db = tgt if tgt is not None else torch.zeros(dy.shape[1], device=dy.device, dtype=torch.float32)
-    L.colsum_bf16(dy, db)
     if tgt is not None:
+        if not _on_side(lambda: L.colsum_bf16(dy, db), dy):
+            L.colsum_bf16(dy, db)
         grad_done(param)
         return None
+    L.colsum_bf16(dy, db)
     return db
 
 
@@ -212,17 +308,22 @@ def _attn_fwd(h, wqkv16, bqkv, wo16, bo, residual, batch, seq, heads):
 
 
 def _attn_bwd(dout, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need, batch, seq, heads, params=(None, None, None, None)):
-    """need = (dh, dWqkv, dbqkv, dWo, dbo); params = (Wqkv, bqkv, Wo, bo) Parameters for in-place gradient accumulation"""
+    """need = (dh, dWqkv, dbqkv, dWo, dbo); params = (Wqkv, bqkv, Wo, bo) Parameters for in-place gradient accumulation.
+    BlockFn clears need[4] when the LayerNorm backward that reads ``dout`` as its residual gradient also sums its columns."""
     e = o.shape[1]
-    dwo = linear_wgrad(dout, o, wo_shape, params[2]) if need[3] else None
-    dbo = bias_grad(dout, params[3]) if need[4] else None
+    # the activation-gradient chain is enqueued before the weight gradients of the same input: with the side stream on
+    # (wgrad_overlap) the chain then gets the SMs first and the weight gradients fill what it leaves idle
     if not (need[0] or need[1] or need[2]):
+        dwo = linear_wgrad(dout, o, wo_shape, params[2]) if need[3] else None
+        dbo = bias_grad(dout, params[3]) if need[4] else None
         return None, None, None, dwo, dbo
     # delta[b, h, q] = sum_d dO O of the attention backward comes out of the proj-dgrad epilogue that produces dO (tcgen05
     # attention path, seq <= 208); longer sequences let the attention entry point run its own delta pass
     fused_delta = seq <= 208 and e % 64 == 0 and _FUSED_DELTA
     delta = torch.empty(batch, heads, seq, device=qkv.device, dtype=torch.float32) if fused_delta else None
     do = linear_dgrad(dout, wo16, rowdot=(o, delta, seq)) if fused_delta else linear_dgrad(dout, wo16)
+    dwo = linear_wgrad(dout, o, wo_shape, params[2]) if need[3] else None
+    dbo = bias_grad(dout, params[3]) if need[4] else None
     # the qkv bias gradient = column sums of dqkv: reduced inside the attention backward kernel while it drains dQ/dK/dV
     tbq = grad_target(params[1]) if need[2] else None
     dbqkv = tbq if tbq is not None else (torch.zeros(qkv.shape[1], device=qkv.device, dtype=torch.float32) if need[2] else None)
@@ -230,8 +331,8 @@ def _attn_bwd(dout, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need, ba
     if tbq is not None:
         grad_done(params[1])
         dbqkv = None
-    dwqkv = linear_wgrad(dqkv, h, wqkv_shape, params[0]) if need[1] else None
     dh = linear_dgrad(dqkv, wqkv16) if need[0] else None
+    dwqkv = linear_wgrad(dqkv, h, wqkv_shape, params[0]) if need[1] else None
     return dh, dwqkv, dbqkv, dwo, dbo
 
 
@@ -242,10 +343,11 @@ def _mlp_fwd(h, w116, b1, w216, b2, residual):
 
 
 def _mlp_bwd(dout, h, z, a, w116, w216, w1_shape, w2_shape, need, params=(None, None, None, None)):
-    """need = (dh, dW1, db1, dW2, db2); params = (W1, b1, W2, b2) Parameters for in-place gradient accumulation"""
-    dw2 = linear_wgrad(dout, a, w2_shape, params[2]) if need[3] else None
-    db2 = bias_grad(dout, params[3]) if need[4] else None
+    """need = (dh, dW1, db1, dW2, db2); params = (W1, b1, W2, b2) Parameters for in-place gradient accumulation.
+    BlockFn clears need[4] when the LayerNorm backward that reads ``dout`` as its residual gradient also sums its columns."""
     if not (need[0] or need[1] or need[2]):
+        dw2 = linear_wgrad(dout, a, w2_shape, params[2]) if need[3] else None
+        db2 = bias_grad(dout, params[3]) if need[4] else None
         return None, None, None, dw2, db2
     # fc1's bias gradient = column sums of dz: reduced inside the dgrad epilogue that produces dz (no pass over dz)
     tb1 = grad_target(params[1]) if need[2] else None
@@ -254,8 +356,10 @@ def _mlp_bwd(dout, h, z, a, w116, w216, w1_shape, w2_shape, need, params=(None, 
     if tb1 is not None:
         grad_done(params[1])
         db1 = None
-    dw1 = linear_wgrad(dz, h, w1_shape, params[0]) if need[1] else None
+    dw2 = linear_wgrad(dout, a, w2_shape, params[2]) if need[3] else None
+    db2 = bias_grad(dout, params[3]) if need[4] else None
     dh = linear_dgrad(dz, w116) if need[0] else None
+    dw1 = linear_wgrad(dz, h, w1_shape, params[0]) if need[1] else None
     return dh, dw1, db1, dw2, db2
 
 
@@ -416,12 +520,18 @@ class BlockFn(Function):
         need_dh2 = need_upstream or n[7] or n[8]
         # ---- MLP branch ----
         P = ctx.params
-        dh2, dw1, db1, dw2, db2 = _mlp_bwd(d_out, h2, z, a, w116, w216, w1_shape, w2_shape, (need_dh2, n[9], n[10], n[11], n[12]), P[8:12])
+        # the two bias gradients that are column sums of the residual-stream gradient (fc2's: of dout; the output
+        # projection's: of d_xa) are taken by the LayerNorm backward that reads the same tensor as its residual gradient,
+        # whenever that kernel runs and the bias owns a persistent arena slot; otherwise a column-sum pass of their own
+        tb2 = grad_target(P[11]) if (n[12] and need_dh2 and _FUSED_BIAS) else None
+        dh2, dw1, db1, dw2, db2 = _mlp_bwd(d_out, h2, z, a, w116, w216, w1_shape, w2_shape, (need_dh2, n[9], n[10], n[11], n[12] and tb2 is None), P[8:12])
         dg2 = db_2 = None
         d_xa = d_out
         if dh2 is not None and (need_upstream or n[7] or n[8]):
             dg2, db_2, ig, ib = _ln_grad_buffers(P[6], P[7], g2c, n[7], n[8])
-            d_xa = L.layernorm_bwd(dh2, xa, g2c, mean2, rstd2, dres=d_out, dgamma=dg2, dbeta=db_2)  # = dout + LN2'(dh2)
+            d_xa = L.layernorm_bwd(dh2, xa, g2c, mean2, rstd2, dres=d_out, dgamma=dg2, dbeta=db_2, dres_colsum=tb2)  # = dout + LN2'(dh2)
+            if tb2 is not None:
+                grad_done(P[11])
             if ig:
                 grad_done(P[6])
                 dg2 = None
@@ -429,15 +539,19 @@ class BlockFn(Function):
                 grad_done(P[7])
                 db_2 = None
         if not need_upstream:
+            side_fence()
             return (None, None, None, None, None, None, None, dg2, db_2, dw1, db1, dw2, db2, None, None)
         # ---- attention branch ----
         need_dh1 = n[0] or n[1] or n[2]
-        dh1, dwqkv, dbqkv, dwo, dbo = _attn_bwd(d_xa, h1, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, (need_dh1, n[3], n[4], n[5], n[6]), batch, seq, heads, P[2:6])
+        tbo = grad_target(P[5]) if (n[6] and need_dh1 and _FUSED_BIAS) else None
+        dh1, dwqkv, dbqkv, dwo, dbo = _attn_bwd(d_xa, h1, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, (need_dh1, n[3], n[4], n[5], n[6] and tbo is None), batch, seq, heads, P[2:6])
         dg1 = db_1 = None
         dx = None
         if dh1 is not None:
             dg1, db_1, ig, ib = _ln_grad_buffers(P[0], P[1], g1c, n[1], n[2])
-            dx = L.layernorm_bwd(dh1, x2, g1c, mean1, rstd1, dres=d_xa, dgamma=dg1, dbeta=db_1)
+            dx = L.layernorm_bwd(dh1, x2, g1c, mean1, rstd1, dres=d_xa, dgamma=dg1, dbeta=db_1, dres_colsum=tbo)
+            if tbo is not None:
+                grad_done(P[5])
             if ig:
                 grad_done(P[0])
                 dg1 = None
@@ -450,6 +564,7 @@ class BlockFn(Function):
                 dx = dx.to(in_dtype)
         else:
             dx = None
+        side_fence()
         return (dx, dg1, db_1, dwqkv, dbqkv, dwo, dbo, dg2, db_2, dw1, db1, dw2, db2, None, None)
 
 
