@@ -102,7 +102,8 @@ void vb_set_gemm_cta_pair(int mode);
 int vb_get_gemm_cta_pair(void);
 /* Tile order of vb_gemm_bf16: 0 (default; env VB_GEMM_DYNAMIC=1 overrides) = every CTA pair strides statically over the
  * tiles, 1 = work stealing: tile indices are drawn from a per-launch device counter, so CTAs that become resident late
- * (SMs held by a concurrent kernel such as an overlapped all-reduce) do not delay the launch. Same results either way. */
+ * (SMs held by a concurrent kernel such as an overlapped all-reduce) do not delay the launch. Same results either way.
+ * Launches issued under CUDA stream capture always use the static order (a replayed graph would reuse the counter). */
 void vb_set_gemm_scheduler(int dynamic);
 int vb_get_gemm_scheduler(void);
 /* Tile width of the CTA-pair kernels: 0 (default; env VB_GEMM_TILE_N=192|256 overrides) = chosen per launch: 192-column
@@ -151,6 +152,14 @@ int vb_attention_bwd_bias(const void* qkv, const void* out, const void* dout, co
 int vb_attention_bwd_with_delta(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias,
                                 const void* workspace, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim,
                                 vb_stream_t stream);
+/* Same, but only the QUERY third of the qkv bias gradient is reduced here: dbias_q[0:E] += column sums of dQ (dbias_q is the
+ * start of the [3*E] bias gradient; its other two thirds are not touched). In exact arithmetic the key third is zero (a
+ * per-query shift of the scores does not change the softmax: sum over keys of dS = 0; the reference's fp32 value is
+ * round-off) and the value third equals the column sums of dout (softmax rows sum to one), which the GEMM that produced
+ * dout delivers from its epilogue (vb_gemm_args.out_colsum). The per-key-tile drain of dV / dK is then stores only. */
+int vb_attention_bwd_with_delta_qbias(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias_q,
+                                      const void* workspace, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim,
+                                      vb_stream_t stream);
 /* Paired attention for the plasticity estimator: runs the core on qkv_a and qkv_b (same shapes) and writes
  * delta = attn(qkv_a) - attn(qkv_b), subtracted in fp32 before the bf16 down-cast. */
 int vb_attention_pair_delta(const void* qkv_a, const void* qkv_b, int64_t ld_qkv, void* delta, int64_t ld_delta,

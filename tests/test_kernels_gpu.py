@@ -441,6 +441,31 @@ def test_attention_bwd_with_precomputed_delta_matches():
     _report("attn_bwd_with_delta", got, ref, atol=2e-3, rtol=2e-2)
 
 
+@pytest.mark.parametrize("batch,seq,heads", [(4, 197, 12), (3, 50, 2), (2, 208, 16)])
+def test_attention_bwd_query_only_bias(batch, seq, heads):
+    """vb_attention_bwd_with_delta_qbias: same dqkv bits as the all-thirds entry; the query third of the bias gradient is the
+    column sum of dQ; the key and value thirds of the buffer are left alone. The identities the caller relies on for those
+    two hold on the kernel's own output: column sums of dK ~ 0 and column sums of dV ~ column sums of dO (against the
+    magnitude of the query third)."""
+    L = _lib()
+    e = heads * 64
+    qkv = _rand(batch * seq, 3 * e, seed=1).bfloat16()
+    out, lse = L.attention_fwd(qkv, batch, seq, heads, 64)
+    do = _rand(batch * seq, e, seed=2).bfloat16()
+    delta = (do.float() * out.float()).view(batch, seq, heads, 64).sum(-1).permute(0, 2, 1).contiguous()
+    db_all = torch.zeros(3 * e, device=DEV)
+    ref = L.attention_bwd(qkv, None, do, lse, batch, seq, heads, 64, dbias=db_all, delta=delta)
+    db_q = torch.full((3 * e,), 7.0, device=DEV)
+    got = L.attention_bwd(qkv, None, do, lse, batch, seq, heads, 64, dbias=db_q, delta=delta, q_bias_only=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    assert torch.equal(db_q[e:], torch.full((2 * e,), 7.0, device=DEV))
+    _report("attn_qbias", (db_q[:e] - 7.0)[None], db_all[None, :e], atol=2e-3 * float(db_all[:e].abs().max()), rtol=1e-4)
+    scale = float(db_all[:e].abs().max())
+    assert float(db_all[e:2 * e].abs().max()) <= 2e-2 * scale, "column sums of dK should vanish"
+    _report("attn_vbias_identity", db_all[None, 2 * e:], do.float().sum(0)[None], atol=2e-2 * scale, rtol=2e-2)
+
+
 def test_attention_pair_delta():
     L = _lib()
     batch, seq, heads, hd = 2, 197, 12, 64

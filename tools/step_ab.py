@@ -4,7 +4,8 @@ timed round-robin (R rounds of S replays each), so box state / clocks / thermals
 Usage: python tools/step_ab.py <model> <batch> <variant> [<variant> ...]
 A variant is a comma-separated list of switches: base (nothing), nooverlap (weight gradients on the main stream), noprio
 (graph captured on a default-priority stream), tile256 (no 192-column GEMM tiles), nofusedbias (stand-alone column sums
-for the proj / fc2 bias gradients), steal (work-stealing GEMM tile scheduler), lag2.
+for the proj / fc2 bias gradients), noqbias (all three thirds of the qkv bias gradient inside the attention backward), steal
+(work-stealing GEMM tile scheduler), lag<N> (blocks the side stream may trail the main chain by).
 Prints ms/step per variant and round, the median, and the parameter difference after 5 steps against the first variant."""
 import os
 import statistics
@@ -28,8 +29,9 @@ def build(variant: str):
     sw = set(variant.split(","))
     os.environ["VB_WGRAD_STREAM"] = "0" if "nooverlap" in sw else "1"
     os.environ["VB_GRAPH_PRIORITY"] = "0" if "noprio" in sw else "1"
-    ops._Side.lag = 2 if "lag2" in sw else 1
+    ops._Side.lag = next((int(t[3:]) for t in sw if t.startswith("lag")), ops._Side.lag)
     ops._FUSED_BIAS = "nofusedbias" not in sw
+    ops._QBIAS = "noqbias" not in sw
     L.lib().vb_set_gemm_tile_n(256 if "tile256" in sw else 0)
     L.lib().vb_set_gemm_scheduler(1 if "steal" in sw else 0)
     torch.manual_seed(0)

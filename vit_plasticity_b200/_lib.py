@@ -100,6 +100,10 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
     ),
+    "vb_attention_bwd_with_delta_qbias": (
+        c_int32,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    ),
     "vb_attention_pair_delta": (
         c_int32,
         [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
@@ -301,16 +305,24 @@ def attention_fwd(qkv, batch, seq, heads, head_dim, *, want_lse=True):
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, batch, seq, heads, head_dim, *, dbias=None, delta=None):
+def attention_bwd(qkv, out, dout, lse, batch, seq, heads, head_dim, *, dbias=None, delta=None, q_bias_only=False):
     """dqkv; with ``dbias`` (f32 [3E], accumulated into) the same kernel also reduces the column sums of dqkv. ``delta``
     (f32 [batch, heads, seq] = rowsum(dout * out) per head, e.g. from the ROWDOT epilogue of the GEMM that produced
-    ``dout``): ``out`` is then not read and no delta pass is launched."""
+    ``dout``): ``out`` is then not read and no delta pass is launched. ``q_bias_only`` (with delta and dbias): only the
+    query third of dbias is reduced here; the caller gets the value third as the column sums of ``dout`` from the GEMM that
+    produced it, and the key third is zero."""
     dqkv = torch.empty_like(qkv)
     if delta is not None:
         _req(delta, torch.float32, "delta")
         assert delta.numel() == batch * heads * seq and delta.is_contiguous()
         if dbias is not None:
             _req(dbias, torch.float32, "dbias")
+        if q_bias_only and dbias is not None:
+            _check(
+                lib().vb_attention_bwd_with_delta_qbias(qkv.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), dbias.data_ptr(), delta.data_ptr(), batch, seq, heads, head_dim, _stream()),
+                "vb_attention_bwd_with_delta_qbias",
+            )
+            return dqkv
         _check(
             lib().vb_attention_bwd_with_delta(qkv.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), _ptr(dbias), delta.data_ptr(), batch, seq, heads, head_dim, _stream()),
             "vb_attention_bwd_with_delta",

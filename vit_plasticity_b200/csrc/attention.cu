@@ -439,7 +439,7 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
 // tcgen05 implementations, used for seq <= 208 (ViT-B/L at 224x224)
 int launch_attention_fwd_tc3(const bf16* qkv, bf16* out, float* lse, int batch, int L, int H, cudaStream_t stream);
 int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
-                             float* dbias, int batch, int L, int H, cudaStream_t stream);
+                             float* dbias, int bias_q_only, int batch, int L, int H, cudaStream_t stream);
 int launch_colsum_bf16(const bf16* x, int64_t ldx, float* out, int rows, int cols, cudaStream_t stream);
 int launch_attention_pair_tc3(const bf16* qkv_a, const bf16* qkv_b, int64_t ld, bf16* delta, int layers, int batch, int L, int H,
                               cudaStream_t stream);
@@ -564,8 +564,20 @@ extern "C" int vb_attention_bwd_with_delta(const void* qkv, const void* dout, co
     VB_CHECK_ARG(head_dim == HD, "vb_attention_bwd_with_delta: head_dim must be 64 (got %d)", head_dim);
     VB_CHECK_ARG(batch > 0 && heads > 0 && seq > 0 && seq <= 208, "vb_attention_bwd_with_delta: seq=%d must be in [1, 208]", seq);
     return launch_attention_bwd_tc3(static_cast<const bf16*>(qkv), nullptr, static_cast<const bf16*>(dout), lse,
-                                    static_cast<float*>(const_cast<void*>(workspace)), static_cast<bf16*>(dqkv), dbias, batch, seq, heads,
+                                    static_cast<float*>(const_cast<void*>(workspace)), static_cast<bf16*>(dqkv), dbias, 0, batch, seq, heads,
                                     static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vb_attention_bwd_with_delta_qbias(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias_q,
+                                                 const void* workspace, int32_t batch, int32_t seq, int32_t heads,
+                                                 int32_t head_dim, vb_stream_t stream_) {
+    using namespace vb;
+    VB_CHECK_ARG(qkv && dout && lse && dqkv && workspace && dbias_q, "vb_attention_bwd_with_delta_qbias: null pointer");
+    VB_CHECK_ARG(head_dim == HD, "vb_attention_bwd_with_delta_qbias: head_dim must be 64 (got %d)", head_dim);
+    VB_CHECK_ARG(batch > 0 && heads > 0 && seq > 0 && seq <= 208, "vb_attention_bwd_with_delta_qbias: seq=%d must be in [1, 208]", seq);
+    return launch_attention_bwd_tc3(static_cast<const bf16*>(qkv), nullptr, static_cast<const bf16*>(dout), lse,
+                                    static_cast<float*>(const_cast<void*>(workspace)), static_cast<bf16*>(dqkv), dbias_q, 1, batch, seq,
+                                    heads, static_cast<cudaStream_t>(stream_));
 }
 
 static int attention_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace,
@@ -580,7 +592,7 @@ static int attention_bwd_dispatch(const void* qkv, const void* out, const void* 
         *dbias_done = true;
         return launch_attention_bwd_tc3(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
                                         static_cast<const bf16*>(dout), lse, static_cast<float*>(workspace),
-                                        static_cast<bf16*>(dqkv), dbias, batch, seq, heads, stream);
+                                        static_cast<bf16*>(dqkv), dbias, 0, batch, seq, heads, stream);
     }
     if (seq <= 208)
         return launch_bwd<13>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(dout),

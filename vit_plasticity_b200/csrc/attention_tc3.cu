@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(KD_THREADS, 1)
 attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const __grid_constant__ CUtensorMap tmKV0, const __grid_constant__ CUtensorMap tmKV1,
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
-                        float* __restrict__ dbias, int L, int H, int n_items, long long* __restrict__ dbg) {
+                        float* __restrict__ dbias, int bias_q_only, int L, int H, int n_items, long long* __restrict__ dbg) {
 #define KD_STAMP(g, slot)                                                                                   \
     do {                                                                                                    \
         if (dbg != nullptr && blockIdx.x == 0 && (g) >= 16 && (g) < 80) dbg[((g)-16) * 16 + (slot)] = clock64(); \
@@ -925,12 +925,16 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar);
         };
-        auto put = [&](bool ok, bf16* dst, float* dcol) {
+        // bias_q_only: the key third of the qkv bias gradient is identically zero (sum over keys of dS = 0: the softmax does
+        // not see a per-query shift of the scores) and the value third equals the column sums of dO (softmax rows sum to
+        // one), which the GEMM that produced dO delivers from its epilogue: only dQ's columns are summed here, and the
+        // per-key-tile drain of dV / dK, which the next tile's first MMA2 waits for, is stores only.
+        auto put = [&](bool ok, bf16* dst, float* dcol, bool sum) {
             if (ok) {
                 store_32cols_bf16(dst, a, 1.f);
                 store_32cols_bf16(dst + 32, a2, 1.f);
             }
-            if (dbias != nullptr) {
+            if (dbias != nullptr && sum) {
                 warp_colsum32_atomic(a, ok, dcol, lane);
                 warp_colsum32_atomic(a2, ok, dcol + 32, lane);
             }
@@ -945,18 +949,18 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 tc_fence_after();
                 const int r = j * 128 + row;  // key
                 load64(KD_COL_DV);
-                put(r < L, dbase + (int64_t)r * ld3 + 2 * E, dbias + 2 * E + hd * HD);
+                put(r < L, dbase + (int64_t)r * ld3 + 2 * E, dbias + 2 * E + hd * HD, !bias_q_only);
                 load64(KD_COL_DK);
                 release(kv_acc_free);
-                put(r < L, dbase + (int64_t)r * ld3 + E, dbias + E + hd * HD);
+                put(r < L, dbase + (int64_t)r * ld3 + E, dbias + E + hd * HD, !bias_q_only);
             }
             mbar_wait(q_acc_ready, n & 1, 77);
             tc_fence_after();
             load64(KD_COL_DQ);
-            put(row < L, dbase + (int64_t)row * ld3, dbias + hd * HD);  // queries 0..127
+            put(row < L, dbase + (int64_t)row * ld3, dbias + hd * HD, true);  // queries 0..127
             load64(KD_COL_DQ + 64);
             release(q_acc_free);
-            put(128 + row < L, dbase + (int64_t)(128 + row) * ld3, dbias + hd * HD);  // queries 128..255
+            put(128 + row < L, dbase + (int64_t)(128 + row) * ld3, dbias + hd * HD, true);  // queries 128..255
         }
     } else if (warp >= B_WARP_TMA) {
     setmaxnreg_dec<32>();
@@ -1309,7 +1313,7 @@ int launch_attention_delta_tc3(const bf16* qkv_a, const bf16* dqkv, int64_t ld, 
 
 // delta: caller workspace, f32 [batch, heads, L]
 int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, float* delta, bf16* dqkv,
-                             float* dbias, int batch, int L, int H, cudaStream_t stream) {
+                             float* dbias, int bias_q_only, int batch, int L, int H, cudaStream_t stream) {
     using namespace attn3;
     CUtensorMap tmQKV, tmDO;
     int rc = make_maps(&tmQKV, qkv, &tmDO, dout, batch, L, H);
@@ -1342,7 +1346,7 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
         long long* dbg = nullptr;
         VB_CHECK_CUDA(cudaMallocManaged(&dbg, 64 * 16 * sizeof(long long)));
         VB_CHECK_CUDA(cudaMemset(dbg, 0, 64 * 16 * sizeof(long long)));
-        attention_bwd_kd_kernel<true><<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, dbg);
+        attention_bwd_kd_kernel<true><<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, bias_q_only, L, H, n_items, dbg);
         VB_CHECK_CUDA(cudaStreamSynchronize(stream));
         const long long t0 = dbg[0];
         printf("[kd timing] g: mma2{waitP< waitP> accfree>} mma1{cfree< cfree>} math{start dsfree> Sready> stores> arrive> ld> math>}\n");
@@ -1355,9 +1359,9 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
         return VB_OK;
     }
     if (early)
-        attention_bwd_kd_kernel<true><<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
+        attention_bwd_kd_kernel<true><<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, bias_q_only, L, H, n_items, nullptr);
     else
-        attention_bwd_kd_kernel<false><<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, L, H, n_items, nullptr);
+        attention_bwd_kd_kernel<false><<<grid, KD_THREADS, KD_SMEM, stream>>>(tmQKV, tmDO, tmKV0, tmKV1, lse, delta, dqkv, dbias, bias_q_only, L, H, n_items, nullptr);
     VB_CHECK_LAUNCH();
     return VB_OK;
 }

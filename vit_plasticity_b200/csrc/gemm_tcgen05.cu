@@ -736,11 +736,16 @@ static int dynamic_enabled() {
     }
     return g_dynamic;
 }
-static int sched_slots(unsigned** cur, unsigned** clear) {
+static int sched_slots(unsigned** cur, unsigned** clear, cudaStream_t stream) {
     int dev = 0;
     VB_CHECK_CUDA(cudaGetDevice(&dev));
     *cur = *clear = nullptr;
     if (!dynamic_enabled() || dev >= 64) return VB_OK;
+    // A captured launch would bake its counter slot into the graph: every replay would find the slot where the previous
+    // replay left it (tiles skipped, wrong results). Launches under stream capture keep the static tile order.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    VB_CHECK_CUDA(cudaStreamIsCapturing(stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone) return VB_OK;
     if (g_sched_ring[dev] == nullptr) {
         VB_CHECK_CUDA(cudaMalloc(&g_sched_ring[dev], SCHED_RING * sizeof(unsigned)));
         VB_CHECK_CUDA(cudaMemset(g_sched_ring[dev], 0, SCHED_RING * sizeof(unsigned)));
@@ -917,7 +922,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     p.n_groups = a->n_groups;
     p.has_out2 = a->out2 != nullptr;
     p.out_colsum = a->out_colsum;
-    rc = sched_slots(&p.sched, &p.sched_clear);
+    rc = sched_slots(&p.sched, &p.sched_clear, stream);
     if (rc) return rc;
 
     // the hot combinations of the training step get an epilogue fixed at compile time, everything else the generic kernel

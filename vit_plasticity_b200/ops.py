@@ -28,6 +28,7 @@ from . import _lib as L
 
 NUM_SMS = 148
 _FUSED_DELTA = os.environ.get("VB_FUSED_DELTA", "1") != "0"  # measurement switch: 0 = stand-alone delta pass
+_QBIAS = os.environ.get("VB_ATTN_QBIAS", "1") != "0"  # measurement switch: 0 = all three thirds of the qkv bias gradient in the attention backward
 _FUSED_BIAS = os.environ.get("VB_FUSED_BIAS", "1") != "0"  # measurement switch: 0 = stand-alone column sums for proj / fc2 bias
 
 # --------------------------------------------------------------------------------------------------
@@ -223,7 +224,8 @@ def linear_dgrad(dy, w16, *, dgelu_z=None, mul=None, colsum=None, rowdot=None):
         # rowdot = (other [m, k_in] bf16, out f32 [m / rows, k_in / 64, rows], rows): per-row dot products of dx with
         # ``other`` over 64-column groups, from the epilogue registers (the attention backward's delta when other = O)
         other, dst, rows = rowdot
-        L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_ROWDOT, aux=other, out=dx, sumsq=dst, rows_per_sample=rows, cols_per_group=64, n_groups=k_in // 64)
+        L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_ROWDOT, aux=other, out=dx, sumsq=dst, rows_per_sample=rows, cols_per_group=64, n_groups=k_in // 64,
+               out_colsum=colsum)
         return dx
     if mul is not None:
         L.gemm(dy, w16, m=m, n=k_in, k=n_out, b_layout=1, epilogue=L.EPI_BF16_MULAUX, aux=mul, out=dx, out_colsum=colsum)
@@ -321,13 +323,16 @@ def _attn_bwd(dout, h, qkv, o, lse, wqkv16, wo16, wqkv_shape, wo_shape, need, ba
     # attention path, seq <= 208); longer sequences let the attention entry point run its own delta pass
     fused_delta = seq <= 208 and e % 64 == 0 and _FUSED_DELTA
     delta = torch.empty(batch, heads, seq, device=qkv.device, dtype=torch.float32) if fused_delta else None
-    do = linear_dgrad(dout, wo16, rowdot=(o, delta, seq)) if fused_delta else linear_dgrad(dout, wo16)
-    dwo = linear_wgrad(dout, o, wo_shape, params[2]) if need[3] else None
-    dbo = bias_grad(dout, params[3]) if need[4] else None
-    # the qkv bias gradient = column sums of dqkv: reduced inside the attention backward kernel while it drains dQ/dK/dV
+    # the qkv bias gradient = column sums of dqkv. Its value third is the column sums of dO (softmax rows sum to one): they
+    # come out of the epilogue of the GEMM that produces dO; its key third is zero (sum over keys of dS = 0); only the query
+    # third is reduced inside the attention backward kernel, while it drains dQ (_QBIAS off / long sequences: all three there)
     tbq = grad_target(params[1]) if need[2] else None
     dbqkv = tbq if tbq is not None else (torch.zeros(qkv.shape[1], device=qkv.device, dtype=torch.float32) if need[2] else None)
-    dqkv = L.attention_bwd(qkv, o, do, lse, batch, seq, heads, e // heads, dbias=dbqkv, delta=delta)
+    qb = fused_delta and dbqkv is not None and _QBIAS
+    do = linear_dgrad(dout, wo16, rowdot=(o, delta, seq), colsum=dbqkv[2 * e:] if qb else None) if fused_delta else linear_dgrad(dout, wo16)
+    dwo = linear_wgrad(dout, o, wo_shape, params[2]) if need[3] else None
+    dbo = bias_grad(dout, params[3]) if need[4] else None
+    dqkv = L.attention_bwd(qkv, o, do, lse, batch, seq, heads, e // heads, dbias=dbqkv, delta=delta, q_bias_only=qb)
     if tbq is not None:
         grad_done(params[1])
         dbqkv = None
