@@ -114,7 +114,7 @@ def grad_done(p) -> None:
 # that might overtake the side stream; the same event waits are what a CUDA-graph capture records as dependencies.
 class _Side:
     enabled = False
-    lag = int(os.environ.get("VB_WGRAD_LAG", "1"))
+    lag = int(os.environ.get("VB_WGRAD_LAG", "2"))  # blocks the side stream may trail by (operands of that many blocks stay alive)
     streams: dict = {}
     keep: list = []  # operands of side-stream kernels enqueued since the last fence
     pending: list = []  # [(event, operands)] of finished blocks, oldest first
