@@ -1,5 +1,10 @@
-"""Kernel-time breakdown of one finetuning step (torch.profiler / CUPTI); prints the top kernels by total time."""
+"""Kernel-time breakdown of one finetuning step (torch.profiler / CUPTI); prints the top kernels by total time.
+The weight-gradient side stream is switched off here (VB_WGRAD_STREAM=0 unless the variable is already set): kernels that run
+concurrently share the SMs, so their individual durations would no longer add up to the step."""
+import os
 import sys
+
+os.environ.setdefault("VB_WGRAD_STREAM", "0")
 from pathlib import Path
 
 import torch
