@@ -606,6 +606,7 @@ def test_side_stream_and_fused_bias_gradients_match_plain_path(name, graphed, mo
     assert float(g_old[k0][e:2 * e].abs().max()) <= 1e-2 * float(g_old[k0].abs().max())  # ... and is round-off on the old one
     worst_p = max((rel_l2(p_new[k], p_old[k]), k) for k in p_old)
     REPORT[f"{name}/side_stream_fused_bias_worst_param_rel_l2_after_3_steps{tag}"] = worst_p[0]
+    _dump_report()
     assert worst_p[0] <= 1e-4, worst_p  # (measured: <= 1e-5 on the 4-layer model, 3.7e-5 on the 24-layer one)
 
 
