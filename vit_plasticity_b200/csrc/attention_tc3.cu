@@ -80,17 +80,19 @@ __device__ __forceinline__ uint8_t* align_smem(uint8_t* raw) {
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
-// 32 fp32 accumulator columns -> 32 bf16 -> 64 contiguous bytes
+// 32 fp32 accumulator columns -> 32 bf16 -> 64 contiguous bytes (dst 32-byte aligned), as two 256-bit stores. Every lane
+// writes its own row, so one store instruction touches 32 different 128-byte lines whatever its width: 256-bit stores halve
+// the LSU wavefronts of the accumulator drain, which share the SM's memory pipeline with the math warps' lse / delta loads
+// and dS^T stores (a math phase that overlaps a drain takes 3 300 - 4 800 cycles instead of 900, profiles/r04_e_kd_timeline.log).
 __device__ __forceinline__ void store_32cols_bf16(bf16* dst, const uint32_t (&a)[32], float mul) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(a[8 * i + 0]) * mul, __uint_as_float(a[8 * i + 1]) * mul);
-        u.y = pack_bf16x2(__uint_as_float(a[8 * i + 2]) * mul, __uint_as_float(a[8 * i + 3]) * mul);
-        u.z = pack_bf16x2(__uint_as_float(a[8 * i + 4]) * mul, __uint_as_float(a[8 * i + 5]) * mul);
-        u.w = pack_bf16x2(__uint_as_float(a[8 * i + 6]) * mul, __uint_as_float(a[8 * i + 7]) * mul);
-        d4[i] = u;
+    for (int i = 0; i < 2; ++i) {
+        uint32_t u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(__uint_as_float(a[16 * i + 2 * j]) * mul, __uint_as_float(a[16 * i + 2 * j + 1]) * mul);
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * i), "r"(u[0]), "r"(u[1]), "r"(u[2]),
+                     "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                     : "memory");
     }
 }
 
