@@ -22,6 +22,7 @@ dbias = torch.zeros(3 * E, device="cuda")
 flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
 
 variants = {
+    "forward": lambda: L.attention_fwd(qkv, B, S, H, 64),
     "no bias gradient": lambda: L.attention_bwd(qkv, None, do, lse, B, S, H, 64, delta=delta),
     "all three thirds in the kernel": lambda: L.attention_bwd(qkv, None, do, lse, B, S, H, 64, dbias=dbias, delta=delta),
     "query third only": lambda: L.attention_bwd(qkv, None, do, lse, B, S, H, 64, dbias=dbias, delta=delta, q_bias_only=True),

@@ -96,6 +96,13 @@ __device__ __forceinline__ void store_32cols_bf16(bf16* dst, const uint32_t (&a)
     }
 }
 
+// 16 bf16 (32 contiguous bytes, dst 32-byte aligned) as ONE 256-bit store (see store_32cols_bf16)
+__device__ __forceinline__ void store_16cols_packed(bf16* dst, const uint32_t (&u)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
+                 "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                 : "memory");
+}
+
 // dst[c] += sum over the warp's 32 lanes (rows) of a[c], c = 0..31: butterfly transpose-reduce (31 shuffles), lane c ends
 // with column c's total and issues one reduction. Rows that must not count are excluded with row_ok.
 __device__ __forceinline__ void warp_colsum32_atomic(const uint32_t (&a)[32], bool row_ok, float* dst, int lane) {
@@ -362,18 +369,10 @@ attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const
                     }
                 }
                 if (store) {
-                    uint4 w0, w1;
-                    w0.x = pack_bf16x2(r[0], r[1]);
-                    w0.y = pack_bf16x2(r[2], r[3]);
-                    w0.z = pack_bf16x2(r[4], r[5]);
-                    w0.w = pack_bf16x2(r[6], r[7]);
-                    w1.x = pack_bf16x2(r[8], r[9]);
-                    w1.y = pack_bf16x2(r[10], r[11]);
-                    w1.z = pack_bf16x2(r[12], r[13]);
-                    w1.w = pack_bf16x2(r[14], r[15]);
-                    uint4* dst = reinterpret_cast<uint4*>(out + (((int64_t)layer * batch + b) * L + q) * E + hd * HD + part * 16);
-                    dst[0] = w0;
-                    dst[1] = w1;
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(r[2 * i], r[2 * i + 1]);
+                    store_16cols_packed(out + (((int64_t)layer * batch + b) * L + q) * E + hd * HD + part * 16, w);
                     if (!PAIR && part == 0 && lse_out != nullptr) lse_out[((int64_t)b * H + hd) * L + q] = m_prev * 0.125f + __logf(tot);
                 }
             }
@@ -758,18 +757,10 @@ attention_perturb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (lane == 0) mbar_arrive(o_free);
             const int q = t * 128 + row;
             if (q < L) {
-                uint4 w0, w1;
-                w0.x = pack_bf16x2(__uint_as_float(o[0]), __uint_as_float(o[1]));
-                w0.y = pack_bf16x2(__uint_as_float(o[2]), __uint_as_float(o[3]));
-                w0.z = pack_bf16x2(__uint_as_float(o[4]), __uint_as_float(o[5]));
-                w0.w = pack_bf16x2(__uint_as_float(o[6]), __uint_as_float(o[7]));
-                w1.x = pack_bf16x2(__uint_as_float(o[8]), __uint_as_float(o[9]));
-                w1.y = pack_bf16x2(__uint_as_float(o[10]), __uint_as_float(o[11]));
-                w1.z = pack_bf16x2(__uint_as_float(o[12]), __uint_as_float(o[13]));
-                w1.w = pack_bf16x2(__uint_as_float(o[14]), __uint_as_float(o[15]));
-                uint4* dst = reinterpret_cast<uint4*>(out + (((int64_t)layer * batch + b) * L + q) * E + hd * HD + part * 16);
-                dst[0] = w0;
-                dst[1] = w1;
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(o[2 * i]), __uint_as_float(o[2 * i + 1]));
+                store_16cols_packed(out + (((int64_t)layer * batch + b) * L + q) * E + hd * HD + part * 16, w);
             }
         }
     }
