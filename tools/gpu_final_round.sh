@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round-end evidence on one GPU box. Part "a": parity tests, the default bench line, the reference arm, step breakdowns,
 # interleaved A/B of the round's switches. Part "b": ncu launch list of the bench command + full captures (each ncu pass only
-# after the same command exited 0 without ncu). Usage: tools/gpu_final_round.sh <tag> a|b      logs: gpurun_out/<tag>_*
+# after the same command exited 0 without ncu); part "c": the attention-only subset of b.
+# Usage: tools/gpu_final_round.sh <tag> a|b|c      logs: gpurun_out/<tag>_*
 tag=${1:-final}; part=${2:-a}
 mkdir -p gpurun_out
 if [ "$part" == "a" ]; then
@@ -18,6 +19,25 @@ if [ "$part" == "a" ]; then
   timeout 300 python tools/profile_step.py 64 > gpurun_out/${tag}_step_breakdown_b64.log 2>&1
   echo "profile_step 64 rc=$?"
   timeout 300 python tools/step_ab.py large 64 base nooverlap,nofusedbias,noqbias 2>&1 | grep -v Warn | tee gpurun_out/${tag}_step_ab_large_b64.log
+elif [ "$part" == "c" ]; then
+  # after a change to the attention kernels only: launch list + full captures of the attention forward / backward
+  BCMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --pairs 0 --sweep-images 0 --no-gpu-eager --skip-eager-roofline"
+  $BCMD > gpurun_out/${tag}_ncu_plain.log 2>&1 &&
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${tag}_launches.csv $BCMD > gpurun_out/${tag}_ncu_list.log 2>&1
+  echo "ncu list rc=$?"
+  NG="$BCMD --no-graph"
+  $NG > gpurun_out/${tag}_ncu_plain2.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_bwd_kd -s 13 -c 1 -o gpurun_out/${tag}_prof_attn_bwd $NG > gpurun_out/${tag}_ncu_full_attn.log 2>&1
+  echo "ncu full (attention bwd) rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_fwd_persistent -s 13 -c 1 -o gpurun_out/${tag}_prof_attn_fwd $NG > gpurun_out/${tag}_ncu_full_attn_fwd.log 2>&1
+  echo "ncu full (attention fwd) rc=$?"
+  for r in prof_attn_bwd prof_attn_fwd; do
+    python tools/summarize_ncu.py full gpurun_out/${tag}_$r.ncu-rep > gpurun_out/${tag}_ncu_full_$r.txt 2>&1
+  done
+  python tools/summarize_ncu.py launches gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_ncu_launch_list_step.txt 2>&1
+  python tools/ncu_hot.py gpurun_out/${tag}_prof_attn_bwd.ncu-rep attention_bwd_kd 45 > gpurun_out/${tag}_ncu_attention_bwd_stall_sites.txt 2>&1
+  rm -f gpurun_out/${tag}_prof_attn_fwd.ncu-rep gpurun_out/${tag}_prof_attn_bwd.ncu-rep
+  ls -la gpurun_out/${tag}_*
 else
   BCMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --pairs 0 --sweep-images 0 --no-gpu-eager --skip-eager-roofline"
   $BCMD > gpurun_out/${tag}_ncu_plain.log 2>&1 &&

@@ -84,7 +84,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // writes its own row, so one store instruction touches 32 different 128-byte lines whatever its width: 256-bit stores halve
 // the LSU wavefronts of the accumulator drain, which share the SM's memory pipeline with the math warps' lse / delta loads
 // and dS^T stores (a math phase that overlaps a drain takes 3 300 - 4 800 cycles instead of 900, profiles/r04_e_kd_timeline.log).
+// c_attn_store128 (measurement only, env VITB200_ATTN_STG128=1): the 128-bit stores these kernels used before, for A/B runs
+// of the same binary on the same box.
+__constant__ int c_attn_store128 = 0;
 __device__ __forceinline__ void store_32cols_bf16(bf16* dst, const uint32_t (&a)[32], float mul) {
+    if (c_attn_store128) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(a[8 * i + 0]) * mul, __uint_as_float(a[8 * i + 1]) * mul);
+            u.y = pack_bf16x2(__uint_as_float(a[8 * i + 2]) * mul, __uint_as_float(a[8 * i + 3]) * mul);
+            u.z = pack_bf16x2(__uint_as_float(a[8 * i + 4]) * mul, __uint_as_float(a[8 * i + 5]) * mul);
+            u.w = pack_bf16x2(__uint_as_float(a[8 * i + 6]) * mul, __uint_as_float(a[8 * i + 7]) * mul);
+            d4[i] = u;
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         uint32_t u[8];
@@ -98,6 +114,12 @@ __device__ __forceinline__ void store_32cols_bf16(bf16* dst, const uint32_t (&a)
 
 // 16 bf16 (32 contiguous bytes, dst 32-byte aligned) as ONE 256-bit store (see store_32cols_bf16)
 __device__ __forceinline__ void store_16cols_packed(bf16* dst, const uint32_t (&u)[8]) {
+    if (c_attn_store128) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        d4[0] = make_uint4(u[0], u[1], u[2], u[3]);
+        d4[1] = make_uint4(u[4], u[5], u[6], u[7]);
+        return;
+    }
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
                  "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
                  : "memory");
@@ -1224,6 +1246,22 @@ attention_bwd_kd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     }
 }
 
+// VITB200_ATTN_STG128=1 (measurement only): copied into the kernels' constant once per device
+static int ensure_store_mode() {
+    static const int want = []() {
+        const char* e = getenv("VITB200_ATTN_STG128");
+        return (e != nullptr && e[0] == '1') ? 1 : 0;
+    }();
+    static bool done[64] = {false};
+    int dev = 0;
+    VB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (want && dev < 64 && !done[dev]) {
+        VB_CHECK_CUDA(cudaMemcpyToSymbol(attn3::c_attn_store128, &want, sizeof(int)));
+        done[dev] = true;
+    }
+    return VB_OK;
+}
+
 template <typename K>
 static int set_smem(K kern, int bytes, bool& done) {
     if (!done) {
@@ -1250,6 +1288,8 @@ int launch_attention_fwd_tc3(const bf16* qkv, bf16* out, float* lse, int batch, 
     int rc = make_maps(&tmQKV, qkv, nullptr, nullptr, batch, L, H);
     if (rc) return rc;
     static bool done = false;
+    rc = ensure_store_mode();
+    if (rc) return rc;
     rc = set_smem(attention_fwd_persistent_kernel<false>, F_SMEM, done);
     if (rc) return rc;
     const int n_items = batch * H;
@@ -1272,6 +1312,8 @@ int launch_attention_pair_tc3(const bf16* qkv_a, const bf16* qkv_b, int64_t ld, 
                             BOX_ROWS, 1, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     static bool done = false;
+    rc = ensure_store_mode();
+    if (rc) return rc;
     rc = set_smem(attention_fwd_persistent_kernel<true>, F_SMEM, done);
     if (rc) return rc;
     const int n_items = layers * batch * H;
@@ -1295,6 +1337,8 @@ int launch_attention_delta_tc3(const bf16* qkv_a, const bf16* dqkv, int64_t ld, 
                             BOX_ROWS, 1, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     static bool done = false;
+    rc = ensure_store_mode();
+    if (rc) return rc;
     rc = set_smem(attention_perturb_kernel, D_SMEM, done);
     if (rc) return rc;
     const int n_items = layers * batch * H;
@@ -1333,6 +1377,8 @@ int launch_attention_bwd_tc3(const bf16* qkv, const bf16* out, const bf16* dout,
         const char* e = getenv("VITB200_ATTN_BWD_EARLY");  // 0: packed operands in place, MMA1 two chunks behind MMA2 (A/B runs)
         return !(e != nullptr && e[0] == '0');
     }();
+    rc = ensure_store_mode();
+    if (rc) return rc;
     rc = early ? set_smem(attention_bwd_kd_kernel<true>, KD_SMEM, done_kd) : set_smem(attention_bwd_kd_kernel<false>, KD_SMEM, done_kd0);
     if (rc) return rc;
     if (dbg_on) {
