@@ -94,6 +94,18 @@ typedef struct vb_gemm_args {
 } vb_gemm_args;
 
 int vb_gemm_bf16(const vb_gemm_args* args, vb_stream_t stream);
+/* How vb_gemm_bf16 would map `args` onto its persistent grid (host arithmetic on shapes / layouts / epilogue only: no pointer
+ * of `args` is read, nothing is launched, no device is needed — without one the grid is sized for 148 SMs). */
+typedef struct vb_gemm_plan_t {
+    int32_t cta_pair;           /* 1: a CTA pair per tile (tcgen05 cta_group::2), 0: one CTA per tile */
+    int32_t tile_m, tile_n;     /* rows x columns of one output tile: 256 or 128 x 256 or 192 */
+    int32_t m_tiles, n_tiles;   /* tiles along M and N */
+    int32_t split_k;            /* K splits (1 unless VB_EPI_F32_ADD) */
+    int32_t k_blocks_per_split; /* 64-deep k-blocks per split */
+    int32_t units;              /* CTAs or CTA pairs the grid is sized for */
+    int32_t waves;              /* ceil(m_tiles * n_tiles * splits / units): what the launch pays for */
+} vb_gemm_plan_t;
+int vb_gemm_plan(const vb_gemm_args* args, vb_gemm_plan_t* plan);
 /* Tile mapping of vb_gemm_bf16: 1 (default; env VB_GEMM_CTA_PAIR=0..3 overrides) = a CTA pair per 256 x 256 tile with
  * tcgen05.mma.cta_group::2 (each SM stages half of the B tile), 0 = one CTA per 128 x 256 tile; 2 / 3 = pairs with the
  * 6-stage / 5-stage shared-memory split forced for every epilogue. Results are bit-identical per output element for

@@ -72,6 +72,57 @@ def test_argument_validation_needs_no_gpu(built):
     assert handle.vb_attention_fwd(None, None, None, 1, 197, 12, 64, None) == 1
 
 
+def test_gemm_plan_tile_width_and_split_k_need_no_gpu(built):
+    """vb_gemm_plan: the mapping vb_gemm_bf16 chooses, as host arithmetic (148 SMs assumed without a device). ViT-B token rows
+    at 64 / 128 / 256 / 512 images per GPU: the N = 768 GEMMs with a 192-column variant (proj / fc2 forward with the residual
+    epilogue, fc1 / qkv dgrad) take 192-column tiles exactly where that saves a wave of the 74 CTA pairs; everything else and
+    ViT-L (N = 1024) stays at 256; weight gradients get the smallest split-K that fills >= 90 % of the last wave."""
+    from vit_plasticity_b200 import _lib as L
+
+    gp = ctypes.sizeof(L.GemmPlan)
+    assert gp == 9 * 4
+    handle = L.lib()
+    before = handle.vb_get_gemm_tile_n(), handle.vb_get_gemm_cta_pair()
+    handle.vb_set_gemm_tile_n(0)
+    handle.vb_set_gemm_cta_pair(1)
+    try:
+        for images, want in ((64, 192), (128, 192), (256, 256), (512, 256)):
+            m = images * 197
+            for kw in (dict(k=768, epilogue=L.EPI_BF16_RESID), dict(k=3072, epilogue=L.EPI_BF16_RESID),
+                       dict(k=3072, b_layout=1, epilogue=L.EPI_BF16), dict(k=2304, b_layout=1, epilogue=L.EPI_BF16)):
+                p = L.gemm_plan(m, 768, **kw)
+                assert (p["cta_pair"], p["tile_m"], p["tile_n"], p["units"]) == (1, 256, want, 74), (images, kw, p)
+                assert p["n_tiles"] == 768 // want and p["m_tiles"] == -(-m // 256)
+                assert p["waves"] == -(-p["m_tiles"] * p["n_tiles"] // 74)
+            # no 192-column variant: the row-dot epilogue (proj dgrad), the GELU epilogue, a dgrad with fused column sums
+            assert L.gemm_plan(m, 768, 768, b_layout=1, epilogue=L.EPI_BF16_ROWDOT)["tile_n"] == 256
+            assert L.gemm_plan(m, 3072, 768, epilogue=L.EPI_BF16_GELU_GRAD)["tile_n"] == 256
+            assert L.gemm_plan(m, 768, 3072, b_layout=1, epilogue=L.EPI_BF16, out_colsum=True)["tile_n"] == 256
+            assert L.gemm_plan(m, 1024, 1024, epilogue=L.EPI_BF16_RESID)["tile_n"] == 256  # ViT-L: 1024 is no multiple of 192
+        # 64 images: 50 row blocks x 3 tiles = 2.03 waves (3 paid) against 50 x 4 tiles of 3/4 the size = 2.7 waves (3 paid)
+        assert L.gemm_plan(64 * 197, 768, 768, epilogue=L.EPI_BF16)["waves"] == 3  # K-major B without residual: 256 only
+        assert L.gemm_plan(64 * 197, 768, 768, epilogue=L.EPI_BF16_RESID)["waves"] == 3
+        # forced widths
+        handle.vb_set_gemm_tile_n(256)
+        assert L.gemm_plan(64 * 197, 768, 768, epilogue=L.EPI_BF16_RESID)["tile_n"] == 256
+        handle.vb_set_gemm_tile_n(192)
+        assert L.gemm_plan(512 * 197, 768, 768, epilogue=L.EPI_BF16_RESID)["tile_n"] == 192
+        handle.vb_set_gemm_tile_n(0)
+        # weight gradients (both operands MN-major, fp32 reduce-add): auto split-K; fc1 at 512 images: 3 x 12 tiles
+        w = L.gemm_plan(3072, 768, 512 * 197, a_layout=1, b_layout=1, epilogue=L.EPI_F32_ADD, split_k=0)
+        assert w["m_tiles"] * w["n_tiles"] == 36 and w["split_k"] >= 2
+        fill = w["m_tiles"] * w["n_tiles"] * w["split_k"] / (w["waves"] * 74)
+        assert fill >= 0.9, w
+        assert w["k_blocks_per_split"] >= 8
+        # a single 128-row block is not paired
+        s1 = L.gemm_plan(100, 768, 768)
+        assert (s1["cta_pair"], s1["tile_m"], s1["units"]) == (0, 128, 148)
+        assert handle.vb_gemm_plan(None, None) == 1 and b"null" in handle.vb_last_error()
+    finally:
+        handle.vb_set_gemm_tile_n(before[0])
+        handle.vb_set_gemm_cta_pair(before[1])
+
+
 def test_sass_is_blackwell_native(built):
     """tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, TMA -> UTMALDG/UTMASTG/UTMAREDG (B200_PROFILING.md)."""
     obj = ROOT / "vit_plasticity_b200" / "csrc" / "gemm_tcgen05.o"

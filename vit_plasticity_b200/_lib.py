@@ -60,6 +60,12 @@ class GemmArgs(Structure):
     ]
 
 
+class GemmPlan(Structure):
+    """Mirror of ``struct vb_gemm_plan_t``."""
+
+    _fields_ = [(n, c_int32) for n in ("cta_pair", "tile_m", "tile_n", "m_tiles", "n_tiles", "split_k", "k_blocks_per_split", "units", "waves")]
+
+
 # name -> (restype, argtypes); checked against `nm -D` by tests/test_cabi.py
 SIGNATURES = {
     "vb_version": (c_int32, []),
@@ -71,6 +77,7 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p],
     ),
+    "vb_gemm_plan": (c_int32, [POINTER(GemmArgs), POINTER(GemmPlan)]),
     "vb_set_gemm_cta_pair": (None, [c_int32]),
     "vb_get_gemm_cta_pair": (c_int32, []),
     "vb_set_gemm_scheduler": (None, [c_int32]),
@@ -260,6 +267,18 @@ def gemm(
     if events is not None:
         end.record()
         events.append((start, end, 2.0 * m * n * k))
+
+
+def gemm_plan(m: int, n: int, k: int, *, a_layout: int = 0, b_layout: int = 0, epilogue: int = EPI_BF16, split_k: int = 1, out_colsum: bool = False) -> dict:
+    """How ``gemm`` would map this shape onto the persistent grid (tile mapping / width, split-K, waves): host arithmetic only,
+    works without a GPU (the grid is then sized for 148 SMs)."""
+    args = GemmArgs()
+    args.m, args.n, args.k = m, n, k
+    args.a_layout, args.b_layout, args.epilogue, args.split_k = a_layout, b_layout, epilogue, split_k
+    args.out_colsum = 1 if out_colsum else None  # only its null-ness matters to the plan; never dereferenced there
+    plan = GemmPlan()
+    _check(lib().vb_gemm_plan(ctypes.byref(args), ctypes.byref(plan)), "vb_gemm_plan")
+    return {name: getattr(plan, name) for name, _ in GemmPlan._fields_}
 
 
 # --------------------------------------------------------------------------------------------------

@@ -790,21 +790,16 @@ extern "C" int vb_get_gemm_tile_n(void) { return vb::tile_n_mode(); }
 extern "C" void vb_set_gemm_scheduler(int dynamic) { vb::g_dynamic = dynamic ? 1 : 0; }
 extern "C" int vb_get_gemm_scheduler(void) { return vb::dynamic_enabled(); }
 
-extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
+// How a GEMM is mapped onto the persistent grid: tile mapping, tile width, split-K. Pure host arithmetic on the shapes (no
+// pointer of `a` is dereferenced, no device is needed: without one the grid is sized for 148 SMs), shared by vb_gemm_bf16 and
+// vb_gemm_plan so that the choices can be inspected and tested without a GPU.
+static void make_plan(const vb_gemm_args* a, vb_gemm_plan_t* plan) {
     using namespace vb;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    VB_CHECK_ARG(a != nullptr, "vb_gemm_bf16: null args");
-    VB_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "vb_gemm_bf16: bad shape m=%d n=%d k=%d", a->m, a->n, a->k);
-    VB_CHECK_ARG(a->a && a->b, "vb_gemm_bf16: null operand");
-    VB_CHECK_ARG(a->a_layout == 0 || a->a_layout == 1, "vb_gemm_bf16: bad a_layout %d", a->a_layout);
-    VB_CHECK_ARG(a->b_layout == 0 || a->b_layout == 1, "vb_gemm_bf16: bad b_layout %d", a->b_layout);
-    VB_CHECK_ARG(a->epilogue >= VB_EPI_BF16 && a->epilogue <= VB_EPI_BF16_ROWDOT, "vb_gemm_bf16: bad epilogue %d",
-                 a->epilogue);
-    VB_CHECK_ARG(a->n % 8 == 0, "vb_gemm_bf16: n=%d must be a multiple of 8", a->n);
     const int epi = a->epilogue;
     // a CTA pair per 256 x 256 tile whenever there is more than one 128-row block to pair up
     const int G = (cta_pair_enabled() != 0 && a->m > BM) ? 2 : 1;
     const int m_tiles = (a->m + BM * G - 1) / (BM * G), k_blocks = (a->k + BK - 1) / BK;
+    const int units = num_sms() / G;
     // Tile width. The N = 768 GEMMs of a ViT-B block (proj / fc2 forward, the fc1 / qkv dgrads) have 3 tiles of 256 columns
     // per row block: at 64 images per GPU that is 150 tiles = 2.03 waves on 74 pairs, a third of the launch spent on the last
     // 3 tiles. 192-column tiles (4 per row block) cost ~0.78 of a 256-column tile each; they are taken when the waves they
@@ -813,7 +808,6 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
     const bool has192 = G == 2 && a->a_layout == 0 && a->n % 192 == 0 &&
                         ((a->b_layout == 0 && epi == VB_EPI_BF16_RESID) || (a->b_layout == 1 && epi == VB_EPI_BF16 && a->out_colsum == nullptr));
     if (has192) {
-        const int units = num_sms() / G;
         const int waves256 = (m_tiles * ((a->n + BN - 1) / BN) + units - 1) / units, waves192 = (m_tiles * (a->n / 192) + units - 1) / units;
         if (tile_n_mode() == 192 || (tile_n_mode() == 0 && 0.78 * waves192 < 0.97 * waves256)) bnt = 192;
     }
@@ -824,7 +818,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
         // wave (fewer splits = fewer fp32 reduce-adds), else the best-filling one; at least 8 k-blocks per split
         split_k = 1;
         if (epi == VB_EPI_F32_ADD) {
-            const int units = num_sms() / G, tiles = m_tiles * n_tiles;
+            const int tiles = m_tiles * n_tiles;
             const int max_split = k_blocks / 8 < 1 ? 1 : (k_blocks / 8 > 64 ? 64 : k_blocks / 8);
             double best = 0.0;
             for (int s = 1; s <= max_split; ++s) {
@@ -838,6 +832,45 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
             }
         }
     }
+    const int sk = split_k > k_blocks ? k_blocks : split_k;
+    const int kb_per_split = (k_blocks + sk - 1) / sk;
+    plan->cta_pair = G == 2 ? 1 : 0;
+    plan->tile_m = BM * G;
+    plan->tile_n = bnt;
+    plan->m_tiles = m_tiles;
+    plan->n_tiles = n_tiles;
+    plan->split_k = split_k;
+    plan->k_blocks_per_split = kb_per_split;
+    plan->units = units;
+    const int work = m_tiles * n_tiles * ((k_blocks + kb_per_split - 1) / kb_per_split);  // every split is non-empty
+    plan->waves = (work + units - 1) / units;
+}
+
+extern "C" int vb_gemm_plan(const vb_gemm_args* a, vb_gemm_plan_t* plan) {
+    using namespace vb;
+    VB_CHECK_ARG(a != nullptr && plan != nullptr, "vb_gemm_plan: null argument");
+    VB_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "vb_gemm_plan: bad shape m=%d n=%d k=%d", a->m, a->n, a->k);
+    VB_CHECK_ARG(a->epilogue >= VB_EPI_BF16 && a->epilogue <= VB_EPI_BF16_ROWDOT, "vb_gemm_plan: bad epilogue %d", a->epilogue);
+    make_plan(a, plan);
+    return VB_OK;
+}
+
+extern "C" int vb_gemm_bf16(const vb_gemm_args* a, vb_stream_t stream_) {
+    using namespace vb;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VB_CHECK_ARG(a != nullptr, "vb_gemm_bf16: null args");
+    VB_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "vb_gemm_bf16: bad shape m=%d n=%d k=%d", a->m, a->n, a->k);
+    VB_CHECK_ARG(a->a && a->b, "vb_gemm_bf16: null operand");
+    VB_CHECK_ARG(a->a_layout == 0 || a->a_layout == 1, "vb_gemm_bf16: bad a_layout %d", a->a_layout);
+    VB_CHECK_ARG(a->b_layout == 0 || a->b_layout == 1, "vb_gemm_bf16: bad b_layout %d", a->b_layout);
+    VB_CHECK_ARG(a->epilogue >= VB_EPI_BF16 && a->epilogue <= VB_EPI_BF16_ROWDOT, "vb_gemm_bf16: bad epilogue %d",
+                 a->epilogue);
+    VB_CHECK_ARG(a->n % 8 == 0, "vb_gemm_bf16: n=%d must be a multiple of 8", a->n);
+    const int epi = a->epilogue;
+    vb_gemm_plan_t plan;
+    make_plan(a, &plan);
+    const int G = plan.cta_pair ? 2 : 1, bnt = plan.tile_n, m_tiles = plan.m_tiles, n_tiles = plan.n_tiles;
+    const int k_blocks = (a->k + BK - 1) / BK, split_k = plan.split_k;
     VB_CHECK_ARG(split_k == 1 || epi == VB_EPI_F32_ADD, "vb_gemm_bf16: split_k > 1 needs VB_EPI_F32_ADD");
     if (epi == VB_EPI_BF16_ROWDOT)
         VB_CHECK_ARG(a->sumsq && a->rows_per_sample > 0 && a->cols_per_group == 64 && a->n % 64 == 0 && a->n_groups == a->n / 64,
