@@ -23,3 +23,6 @@ if [ "$2" == "ncu" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_bwd_ -s 13 -c 2 -o gpurun_out/${tag}_prof_attn_bwd $BCMD > gpurun_out/${tag}_ncu_full_attn.log 2>&1
   echo "ncu full (attention bwd) rc=$?"
 fi
+# per-kernel regression guard: this run's kernel_bench log against the last kept profiles/*kernel_bench*.log, both normalised
+# by their torch controls (run it here or on the CPU box; exit code 1 = some kernel is > 5 % slower)
+python tools/kernel_regression.py gpurun_out/${tag}_kernel_bench.log; echo "kernel regression guard rc=$?"
