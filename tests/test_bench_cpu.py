@@ -54,3 +54,26 @@ def test_reference_arm_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # the same `config` object the B200 arm prints for this workload
     assert line["config"] == bench.finetune_config("base", 512, 1, [], 85806346, "strong")
+
+
+def test_kernel_regression_guard_on_kept_logs():
+    """tools/kernel_regression.py on logs kept under profiles/: round 1's drift of the attention forward (236 -> 263 us while the
+    torch controls of the same runs moved by 5 %) is flagged, the step from the end of round 1 to the start of round 2 is
+    clean, and the final library against the start of round 2 shows the attention backward more than 25 % faster."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    tool, prof = str(root / "tools" / "kernel_regression.py"), root / "profiles"
+
+    def run(new, base):
+        return subprocess.run([sys.executable, tool, str(prof / new), str(prof / base)], capture_output=True, text=True)
+
+    drift = run("r02_z_kernel_bench.log", "r01_m_kernel_bench.log")
+    assert drift.returncode == 1 and "attention fwd" in drift.stdout.split("FAIL")[-1]
+    clean = run("r03_a_kernel_bench.log", "r02_z_kernel_bench.log")
+    assert clean.returncode == 0 and "OK: no kernel regressed" in clean.stdout
+    final = run("r04_g_kernel_bench.log", "r03_a_kernel_bench.log")
+    line = next(l for l in final.stdout.splitlines() if l.startswith("attention bwd"))
+    assert float(line.rsplit("normalised x", 1)[1].split()[0]) < 0.75, line
